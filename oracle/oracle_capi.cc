@@ -1,0 +1,770 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see orc_common.h).
+//
+// extern "C" surface of the CPU oracle, bound from Python with ctypes
+// (tests/oracle_binding.py). Everything here is a thin adapter around the
+// restatements in orc_*.h.
+
+#include "orc_euler.h"
+#include "orc_integrator.h"
+#include "orc_mesh.h"
+#include "orc_module.h"
+#include "orc_sparsity.h"
+
+#include <cstring>
+#include <memory>
+#include <string>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+namespace
+{
+  thread_local std::string last_error;
+
+  template <typename F>
+  int guarded(const F &f)
+  {
+    try {
+      f();
+      return 0;
+    } catch (const Restart &) {
+      return 1;
+    } catch (const std::exception &e) {
+      last_error = e.what();
+      return -1;
+    }
+  }
+
+  struct OfflineBase {
+    virtual ~OfflineBase() = default;
+    int dimension = 0;
+  };
+
+  template <int dim>
+  struct OfflineHolder : OfflineBase {
+    OfflineHolder() { this->dimension = dim; }
+    CartesianMesh<dim> mesh; /* only valid if has_mesh */
+    bool has_mesh = false;
+    OfflineData<dim> od;
+  };
+
+  euler::Parameters make_params(const double *p)
+  {
+    /* layout documented in tests/oracle_binding.py: EULER_PARAM_FIELDS */
+    euler::Parameters prm;
+    prm.gamma = p[0];
+    prm.reference_density = p[1];
+    prm.vacuum_state_relaxation_small = p[2];
+    prm.vacuum_state_relaxation_large = p[3];
+    prm.riemann_newton_tolerance = p[4];
+    prm.riemann_newton_max_iterations = (unsigned int)p[5];
+    prm.indicator_evc_factor = p[6];
+    prm.limiter_iterations = (unsigned int)p[7];
+    prm.limiter_newton_tolerance = p[8];
+    prm.limiter_newton_max_iterations = (unsigned int)p[9];
+    prm.limiter_relaxation_factor = p[10];
+    prm.expensive_bounds_check = p[11] != 0.;
+    return prm;
+  }
+
+  struct SimBase {
+    virtual ~SimBase() = default;
+    virtual int k() const = 0;
+    virtual unsigned int n() const = 0;
+    virtual std::size_t nnz() const = 0;
+    virtual void interpolate(double t, int slot) = 0;
+    virtual void set_U(int slot, const double *U) = 0;
+    virtual void get_U(int slot, double *U) const = 0;
+    virtual void get_prec(int slot, double *p) const = 0;
+    virtual void prepare_state(int slot, double t) = 0;
+    virtual double hyp_step(int old_slot,
+                            int stages,
+                            const int *stage_slots,
+                            const double *weights,
+                            int new_slot,
+                            double tau,
+                            double tau_max) = 0;
+    virtual double ti_step(double t, double t_final) = 0;
+    virtual void set_cfl(double cfl) = 0;
+    virtual void set_strategy(int raise) = 0;
+    virtual void configure_ti(int scheme, double cfl_min, double cfl_max, int recovery) = 0;
+    virtual void get_scratch(int what, double *out) const = 0;
+    virtual void counters(unsigned int *restarts, unsigned int *warnings) const = 0;
+    virtual double last_tau_max() const = 0;
+    virtual void errors(double t, double *out3) = 0;
+  };
+
+  template <int dim>
+  struct EulerSim : SimBase {
+    using Sys = euler::System<dim>;
+    using Desc = Description<Sys,
+                             euler::RiemannSolver<dim>,
+                             euler::Indicator<dim>,
+                             euler::Limiter<dim>>;
+    using Module = HyperbolicModule<Desc, dim>;
+    using SV = typename Module::StateVector;
+
+    OfflineHolder<dim> *off;
+    Sys sys;
+    euler::InitialValues<dim> iv;
+    std::unique_ptr<Module> module;
+    std::unique_ptr<TimeIntegrator<Desc, dim>> ti;
+    std::vector<SV> slots; /* slot 0 = the state vector of the time loop */
+
+    EulerSim(OfflineHolder<dim> *o, const euler::Parameters &prm)
+        : off(o)
+        , sys(prm)
+        , iv(sys)
+    {
+    }
+
+    void finalize()
+    {
+      iv.transform.normalize();
+      module.reset(new Module(off->od, sys, [this](const Vec<dim> &x, double t) {
+        return iv.initial_state(x, t);
+      }));
+      module->prepare();
+      ti.reset(new TimeIntegrator<Desc, dim>(*module));
+      ti->prepare();
+      slots.resize(6);
+      for (auto &s : slots)
+        s.reinit(off->od.n_owned);
+    }
+
+    int k() const override { return Sys::k; }
+    unsigned int n() const override { return off->od.n_owned; }
+    std::size_t nnz() const override { return off->od.cols.size(); }
+
+    void positions_required() const
+    {
+      if (!off->has_mesh)
+        throw std::runtime_error("oracle: offline data has no mesh positions");
+    }
+
+    void interpolate(double t, int slot) override
+    {
+      positions_required();
+      auto &U = slots[slot].U;
+      for (unsigned int i = 0; i < off->od.n_owned; ++i) {
+        const auto s = iv.initial_state(off->mesh.position(i), t);
+        for (int c = 0; c < Sys::k; ++c)
+          U[std::size_t(i) * Sys::k + c] = s[c];
+      }
+    }
+
+    void set_U(int slot, const double *U) override
+    {
+      std::memcpy(slots[slot].U.data(), U, slots[slot].U.size() * sizeof(double));
+    }
+    void get_U(int slot, double *U) const override
+    {
+      std::memcpy(U, slots[slot].U.data(), slots[slot].U.size() * sizeof(double));
+    }
+    void get_prec(int slot, double *p) const override
+    {
+      std::memcpy(p, slots[slot].prec.data(), slots[slot].prec.size() * sizeof(double));
+    }
+    void prepare_state(int slot, double t) override
+    {
+      module->prepare_state_vector(slots[slot], t);
+    }
+    double hyp_step(int old_slot,
+                    int stages,
+                    const int *stage_slots,
+                    const double *weights,
+                    int new_slot,
+                    double tau,
+                    double tau_max) override
+    {
+      std::vector<const SV *> st;
+      std::vector<double> w;
+      for (int s = 0; s < stages; ++s) {
+        st.push_back(&slots[stage_slots[s]]);
+        w.push_back(weights[s]);
+      }
+      return module->step(slots[old_slot], st, w, slots[new_slot], tau, tau_max);
+    }
+    double ti_step(double t, double t_final) override
+    {
+      return ti->step(slots[0], t, t_final);
+    }
+    void set_cfl(double cfl) override { module->cfl(cfl); }
+    void set_strategy(int raise) override
+    {
+      module->id_violation_strategy_ = raise ? IDViolationStrategy::raise_exception
+                                             : IDViolationStrategy::warn;
+    }
+    void configure_ti(int scheme, double cfl_min, double cfl_max, int recovery) override
+    {
+      ti->time_stepping_scheme_ = TimeSteppingScheme(scheme);
+      ti->cfl_min_ = cfl_min;
+      ti->cfl_max_ = cfl_max;
+      ti->cfl_recovery_strategy_ = CFLRecoveryStrategy(recovery);
+      ti->prepare();
+    }
+    void get_scratch(int what, double *out) const override
+    {
+      const std::vector<double> *v = nullptr;
+      switch (what) {
+      case 0: v = &module->alpha(); break;
+      case 1: v = &module->dij(); break;
+      case 2: v = &module->lij(); break;
+      case 3: v = &module->lij_next(); break;
+      case 4: v = &module->pij(); break;
+      case 5: v = &module->r(); break;
+      case 6: v = &module->bounds(); break;
+      default: throw std::runtime_error("oracle: unknown scratch id");
+      }
+      std::memcpy(out, v->data(), v->size() * sizeof(double));
+    }
+    void counters(unsigned int *restarts, unsigned int *warnings) const override
+    {
+      *restarts = module->n_restarts();
+      *warnings = module->n_warnings();
+    }
+    double last_tau_max() const override { return module->last_tau_max(); }
+
+    /* time_loop.template.h:690-832 with all components, normalized */
+    void errors(double t, double *out3) override
+    {
+      positions_required();
+      module->prepare_state_vector(slots[0], t);
+      const unsigned int n = off->od.n_owned;
+      std::vector<double> analytic(std::size_t(n) * Sys::k);
+      for (unsigned int i = 0; i < n; ++i) {
+        const auto s = iv.initial_state(off->mesh.position(i), t);
+        for (int c = 0; c < Sys::k; ++c)
+          analytic[std::size_t(i) * Sys::k + c] = s[c];
+      }
+      double linf = 0., l1 = 0., l2 = 0.;
+      std::vector<double> a(n), e(n);
+      for (int c = 0; c < Sys::k; ++c) {
+        for (unsigned int i = 0; i < n; ++i) {
+          a[i] = analytic[std::size_t(i) * Sys::k + c];
+          e[i] = slots[0].U[std::size_t(i) * Sys::k + c] - a[i];
+        }
+        const auto na = q1_norms<dim>(off->mesh, a);
+        const auto ne = q1_norms<dim>(off->mesh, e);
+        linf += ne[0] / na[0];
+        l1 += ne[1] / na[1];
+        l2 += ne[2] / na[2];
+      }
+      out3[0] = linf;
+      out3[1] = l1;
+      out3[2] = l2;
+    }
+  };
+} // namespace
+
+
+extern "C" {
+
+const char *orc_last_error() { return last_error.c_str(); }
+
+int orc_uses_vcl()
+{
+#ifdef ORC_USE_VCL
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+int orc_max_threads()
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+double orc_pow(double x, double b) { return orc::pow(x, b); }
+
+/* ---- unit level: Euler ------------------------------------------------ */
+
+/* rd = (rho, u, p); out = (p*_two_rarefaction, p*_failsafe, p_2, phi(p_2),
+ * lambda_max, a_i, a_j); tests/euler/riemann_solver.cc */
+int orc_euler_riemann(const double *params,
+                      const double *state_i,
+                      const double *state_j,
+                      double *out)
+{
+  return guarded([&] {
+    euler::System<1> sys(make_params(params));
+    euler::RiemannSolver<1> rs(sys);
+    auto rd = [&](const double *s) {
+      std::array<double, 4> r{{s[0], s[1], s[2], std::sqrt(sys.gamma * s[2] / s[0])}};
+      return r;
+    };
+    const auto rd_i = rd(state_i), rd_j = rd(state_j);
+    euler::RiemannTrace tr;
+    rs.compute(rd_i, rd_j, &tr);
+    out[0] = tr.p_star_two_rarefaction;
+    out[1] = tr.p_star_failsafe;
+    out[2] = tr.p_2;
+    out[3] = tr.phi_p_2;
+    out[4] = tr.lambda_max;
+    out[5] = rd_i[3];
+    out[6] = rd_j[3];
+  });
+}
+
+/* full state version: lambda_max(U_i, U_j, n_ij) in dim dimensions */
+int orc_euler_riemann_states(int dim,
+                             const double *params,
+                             const double *U_i,
+                             const double *U_j,
+                             const double *n_ij,
+                             double *lambda_max)
+{
+  return guarded([&] {
+    auto run = [&](auto dimc) {
+      constexpr int d = decltype(dimc)::value;
+      euler::System<d> sys(make_params(params));
+      euler::RiemannSolver<d> rs(sys);
+      typename euler::System<d>::state_type a, b;
+      Vec<d> n;
+      for (int c = 0; c < d + 2; ++c) {
+        a[c] = U_i[c];
+        b[c] = U_j[c];
+      }
+      for (int c = 0; c < d; ++c)
+        n[c] = n_ij[c];
+      *lambda_max = rs.compute(a, b, n);
+    };
+    if (dim == 1)
+      run(std::integral_constant<int, 1>());
+    else if (dim == 2)
+      run(std::integral_constant<int, 2>());
+    else
+      run(std::integral_constant<int, 3>());
+  });
+}
+
+/* dim = 1 limiter; out: l, success, t_l_start, t_r_start, n_rounds,
+ * then per round (t_l, t_r, psi_l, psi_r); tests/euler/limiter.cc */
+int orc_euler_limiter(int dim,
+                      const double *params,
+                      const double *U,
+                      const double *P,
+                      const double *bounds,
+                      double *out)
+{
+  return guarded([&] {
+    auto run = [&](auto dimc) {
+      constexpr int d = decltype(dimc)::value;
+      euler::System<d> sys(make_params(params));
+      euler::Limiter<d> lim(sys);
+      typename euler::System<d>::state_type u, p;
+      for (int c = 0; c < d + 2; ++c) {
+        u[c] = U[c];
+        p[c] = P[c];
+      }
+      typename euler::System<d>::bounds_type b{{bounds[0], bounds[1], bounds[2]}};
+      bool success;
+      euler::LimiterTrace tr;
+      const double l = lim.limit(b, u, p, success, 0., 1., &tr);
+      out[0] = l;
+      out[1] = success ? 1. : 0.;
+      out[2] = tr.t_l_start;
+      out[3] = tr.t_r_start;
+      out[4] = tr.n_rounds;
+      for (int r = 0; r < tr.n_rounds; ++r) {
+        out[5 + 4 * r + 0] = tr.t_l[r];
+        out[5 + 4 * r + 1] = tr.t_r[r];
+        out[5 + 4 * r + 2] = tr.psi_l[r];
+        out[5 + 4 * r + 3] = tr.psi_r[r];
+      }
+      out[5 + 4 * 8] = sys.specific_entropy(u);
+    };
+    if (dim == 1)
+      run(std::integral_constant<int, 1>());
+    else if (dim == 2)
+      run(std::integral_constant<int, 2>());
+    else
+      run(std::integral_constant<int, 3>());
+  });
+}
+
+/* tests/euler/hyperbolic_system.cc: out is filled in print order:
+ * momentum[dim], internal_energy, internal_energy_derivative[k], pressure,
+ * specific_entropy, harten_entropy, harten_entropy_derivative[k],
+ * mathematical_entropy, mathematical_entropy_derivative[k], f[k*dim] */
+int orc_euler_system_quantities(int dim, const double *params, const double *U, double *out)
+{
+  return guarded([&] {
+    auto run = [&](auto dimc) {
+      constexpr int d = decltype(dimc)::value;
+      constexpr int k = d + 2;
+      euler::System<d> sys(make_params(params));
+      typename euler::System<d>::state_type u;
+      for (int c = 0; c < k; ++c)
+        u[c] = U[c];
+      int o = 0;
+      const auto m = sys.momentum(u);
+      for (int c = 0; c < d; ++c)
+        out[o++] = m[c];
+      out[o++] = sys.internal_energy(u);
+      const auto ied = sys.internal_energy_derivative(u);
+      for (int c = 0; c < k; ++c)
+        out[o++] = ied[c];
+      out[o++] = sys.pressure(u);
+      out[o++] = sys.specific_entropy(u);
+      out[o++] = sys.harten_entropy(u);
+      const auto hed = sys.harten_entropy_derivative(u);
+      for (int c = 0; c < k; ++c)
+        out[o++] = hed[c];
+      out[o++] = sys.mathematical_entropy(u);
+      const auto med = sys.mathematical_entropy_derivative(u);
+      for (int c = 0; c < k; ++c)
+        out[o++] = med[c];
+      const auto f = sys.f(u);
+      for (int c = 0; c < k; ++c)
+        for (int e = 0; e < d; ++e)
+          out[o++] = f[c][e];
+    };
+    if (dim == 1)
+      run(std::integral_constant<int, 1>());
+    else if (dim == 2)
+      run(std::integral_constant<int, 2>());
+    else
+      run(std::integral_constant<int, 3>());
+  });
+}
+
+/* ---- unit level: SIMD sparsity layout ---------------------------------- */
+
+/* outputs sized nnz; row_starts sized n_rows+1 (as size_t -> uint64) */
+int orc_sparsity_simd(unsigned int n_rows,
+                      const unsigned int *row_ptr,
+                      const unsigned int *cols,
+                      unsigned int n_internal,
+                      unsigned int simd_length,
+                      unsigned long long *row_starts,
+                      unsigned int *column_indices,
+                      unsigned int *indices_transposed)
+{
+  return guarded([&] {
+    std::vector<unsigned int> rp(row_ptr, row_ptr + n_rows + 1);
+    std::vector<unsigned int> cl(cols, cols + rp.back());
+    SparsityPatternSIMD sp;
+    sp.reinit(n_internal, simd_length, rp, cl);
+    for (unsigned int i = 0; i <= n_rows; ++i)
+      row_starts[i] = sp.row_starts[i];
+    std::memcpy(column_indices, sp.column_indices.data(), cl.size() * sizeof(unsigned int));
+    std::memcpy(indices_transposed, sp.indices_transposed.data(), cl.size() * sizeof(unsigned int));
+  });
+}
+
+/* ---- offline data ------------------------------------------------------- */
+
+/* Cartesian (optionally masked) Q1 mesh. box_ids[2*dim]: boundary id of the
+ * outer box faces (x-,x+,y-,y+,z-,z+); masked_id: id of faces bordering an
+ * inactive cell inside the box. */
+void *orc_offline_assemble(int dim,
+                           const unsigned int *n_cells,
+                           const double *origin,
+                           const double *h,
+                           const unsigned char *mask,
+                           const int *box_ids,
+                           int masked_id)
+{
+  void *result = nullptr;
+  const int rc = guarded([&] {
+    auto run = [&](auto dimc) {
+      constexpr int d = decltype(dimc)::value;
+      auto *holder = new OfflineHolder<d>();
+      auto &mesh = holder->mesh;
+      std::size_t ncell = 1;
+      for (int c = 0; c < d; ++c) {
+        mesh.n_cells[c] = n_cells[c];
+        mesh.origin[c] = origin[c];
+        mesh.h[c] = h[c];
+        ncell *= n_cells[c];
+      }
+      if (mask)
+        mesh.cell_mask.assign(mask, mask + ncell);
+      std::array<int, 2 * d> ids;
+      for (int f = 0; f < 2 * d; ++f)
+        ids[f] = box_ids[f];
+      auto nc = mesh.n_cells;
+      mesh.boundary_id = [ids, nc, masked_id](const std::array<unsigned int, d> &cell, int f) {
+        const int fd = f / 2, side = f % 2;
+        const bool outer = side ? (cell[fd] + 1 == nc[fd]) : (cell[fd] == 0);
+        return outer ? ids[f] : masked_id;
+      };
+      holder->od = assemble_offline_data<d>(mesh);
+      holder->has_mesh = true;
+      result = static_cast<OfflineBase *>(holder);
+    };
+    if (dim == 1)
+      run(std::integral_constant<int, 1>());
+    else if (dim == 2)
+      run(std::integral_constant<int, 2>());
+    else
+      run(std::integral_constant<int, 3>());
+  });
+  return rc == 0 ? result : nullptr;
+}
+
+/* Build from caller-provided arrays (e.g. the product's generator output in
+ * its own numbering). boundary arrays are structure-of-arrays. positions may
+ * be NULL. */
+void *orc_offline_from_arrays(int dim,
+                              unsigned int n,
+                              const unsigned int *row_ptr,
+                              const unsigned int *cols,
+                              const double *mij,
+                              const double *cij,
+                              const double *mi,
+                              double measure,
+                              unsigned int n_boundary,
+                              const unsigned int *b_index,
+                              const double *b_normal,
+                              const int *b_id,
+                              const double *b_position,
+                              unsigned int n_pairs,
+                              const unsigned int *pairs /* (i,col,j) triples */)
+{
+  void *result = nullptr;
+  const int rc = guarded([&] {
+    auto run = [&](auto dimc) {
+      constexpr int d = decltype(dimc)::value;
+      auto *holder = new OfflineHolder<d>();
+      auto &od = holder->od;
+      od.n_owned = n;
+      od.row_ptr.assign(row_ptr, row_ptr + n + 1);
+      const std::size_t nnz = od.row_ptr.back();
+      od.cols.assign(cols, cols + nnz);
+      od.mij.assign(mij, mij + nnz);
+      od.cij.assign(cij, cij + nnz * d);
+      od.mi.assign(mi, mi + n);
+      od.mi_inv.resize(n);
+      for (unsigned int i = 0; i < n; ++i)
+        od.mi_inv[i] = 1. / mi[i];
+      od.measure_of_omega = measure;
+      od.build_transposed();
+      for (unsigned int b = 0; b < n_boundary; ++b) {
+        BoundaryDescription<d> bd;
+        bd.i = b_index[b];
+        for (int c = 0; c < d; ++c) {
+          bd.normal[c] = b_normal[b * d + c];
+          bd.position[c] = b_position ? b_position[b * d + c] : 0.;
+        }
+        bd.normal_mass = 0.;
+        bd.boundary_mass = 0.;
+        bd.id = b_id[b];
+        od.boundary_map.push_back(bd);
+      }
+      for (unsigned int p = 0; p < n_pairs; ++p)
+        od.coupling_boundary_pairs.push_back({pairs[3 * p], pairs[3 * p + 1], pairs[3 * p + 2]});
+      result = static_cast<OfflineBase *>(holder);
+    };
+    if (dim == 1)
+      run(std::integral_constant<int, 1>());
+    else if (dim == 2)
+      run(std::integral_constant<int, 2>());
+    else
+      run(std::integral_constant<int, 3>());
+  });
+  return rc == 0 ? result : nullptr;
+}
+
+void orc_offline_destroy(void *h) { delete static_cast<OfflineBase *>(h); }
+
+#define WITH_OFFLINE(h, body)                                                  \
+  do {                                                                         \
+    OfflineBase *base__ = static_cast<OfflineBase *>(h);                       \
+    if (base__->dimension == 1) {                                                    \
+      auto &H = *static_cast<OfflineHolder<1> *>(base__);                      \
+      constexpr int D = 1;                                                     \
+      (void)D;                                                                 \
+      body                                                                     \
+    } else if (base__->dimension == 2) {                                             \
+      auto &H = *static_cast<OfflineHolder<2> *>(base__);                      \
+      constexpr int D = 2;                                                     \
+      (void)D;                                                                 \
+      body                                                                     \
+    } else {                                                                   \
+      auto &H = *static_cast<OfflineHolder<3> *>(base__);                      \
+      constexpr int D = 3;                                                     \
+      (void)D;                                                                 \
+      body                                                                     \
+    }                                                                          \
+  } while (0)
+
+/* sizes: out = (n_dofs, nnz, n_boundary, n_pairs) */
+void orc_offline_sizes(void *h, unsigned long long *out)
+{
+  WITH_OFFLINE(h, {
+    out[0] = H.od.n_owned;
+    out[1] = H.od.cols.size();
+    out[2] = H.od.boundary_map.size();
+    out[3] = H.od.coupling_boundary_pairs.size();
+  });
+}
+
+void orc_offline_get(void *h,
+                     unsigned int *row_ptr,
+                     unsigned int *cols,
+                     unsigned int *transposed,
+                     double *mij,
+                     double *cij,
+                     double *mi,
+                     double *measure,
+                     unsigned int *b_index,
+                     double *b_normal,
+                     double *b_masses,
+                     int *b_id,
+                     double *b_position,
+                     unsigned int *pairs,
+                     double *positions)
+{
+  WITH_OFFLINE(h, {
+    const auto &od = H.od;
+    std::memcpy(row_ptr, od.row_ptr.data(), od.row_ptr.size() * sizeof(unsigned int));
+    std::memcpy(cols, od.cols.data(), od.cols.size() * sizeof(unsigned int));
+    std::memcpy(transposed, od.transposed.data(), od.transposed.size() * sizeof(unsigned int));
+    std::memcpy(mij, od.mij.data(), od.mij.size() * sizeof(double));
+    std::memcpy(cij, od.cij.data(), od.cij.size() * sizeof(double));
+    std::memcpy(mi, od.mi.data(), od.mi.size() * sizeof(double));
+    *measure = od.measure_of_omega;
+    for (std::size_t b = 0; b < od.boundary_map.size(); ++b) {
+      const auto &bd = od.boundary_map[b];
+      b_index[b] = bd.i;
+      b_id[b] = bd.id;
+      b_masses[2 * b] = bd.normal_mass;
+      b_masses[2 * b + 1] = bd.boundary_mass;
+      for (int c = 0; c < D; ++c) {
+        b_normal[b * D + c] = bd.normal[c];
+        b_position[b * D + c] = bd.position[c];
+      }
+    }
+    for (std::size_t p = 0; p < od.coupling_boundary_pairs.size(); ++p) {
+      pairs[3 * p] = od.coupling_boundary_pairs[p].i;
+      pairs[3 * p + 1] = od.coupling_boundary_pairs[p].col_idx;
+      pairs[3 * p + 2] = od.coupling_boundary_pairs[p].j;
+    }
+    if (positions && H.has_mesh)
+      for (unsigned int i = 0; i < od.n_owned; ++i) {
+        const auto x = H.mesh.position(i);
+        for (int c = 0; c < D; ++c)
+          positions[std::size_t(i) * D + c] = x[c];
+      }
+  });
+}
+
+/* ---- simulation handle (module + integrator) ---------------------------- */
+
+/* iv = (kind, direction[3], position[3], prim/left[3], right[3], mach, beta) */
+void *orc_sim_create_euler(void *offline, const double *params, const double *iv)
+{
+  void *result = nullptr;
+  const int rc = guarded([&] {
+    WITH_OFFLINE(offline, {
+      auto *sim = new EulerSim<D>(&H, make_params(params));
+      sim->iv.kind = euler::InitialStateKind(int(iv[0]));
+      for (int c = 0; c < D; ++c) {
+        sim->iv.transform.direction[c] = iv[1 + c];
+        sim->iv.transform.position[c] = iv[4 + c];
+      }
+      for (int c = 0; c < 3; ++c) {
+        sim->iv.primitive[c] = iv[7 + c];
+        sim->iv.primitive_left[c] = iv[7 + c];
+        sim->iv.primitive_right[c] = iv[10 + c];
+      }
+      sim->iv.mach_number = iv[13];
+      sim->iv.beta = iv[14];
+      sim->finalize();
+      result = static_cast<SimBase *>(sim);
+    });
+  });
+  return rc == 0 ? result : nullptr;
+}
+
+void orc_sim_destroy(void *s) { delete static_cast<SimBase *>(s); }
+
+int orc_sim_k(void *s) { return static_cast<SimBase *>(s)->k(); }
+
+int orc_sim_interpolate(void *s, double t, int slot)
+{
+  return guarded([&] { static_cast<SimBase *>(s)->interpolate(t, slot); });
+}
+int orc_sim_set_U(void *s, int slot, const double *U)
+{
+  return guarded([&] { static_cast<SimBase *>(s)->set_U(slot, U); });
+}
+int orc_sim_get_U(void *s, int slot, double *U)
+{
+  return guarded([&] { static_cast<SimBase *>(s)->get_U(slot, U); });
+}
+int orc_sim_get_prec(void *s, int slot, double *p)
+{
+  return guarded([&] { static_cast<SimBase *>(s)->get_prec(slot, p); });
+}
+int orc_sim_prepare_state(void *s, int slot, double t)
+{
+  return guarded([&] { static_cast<SimBase *>(s)->prepare_state(slot, t); });
+}
+int orc_sim_hyp_step(void *s,
+                     int old_slot,
+                     int stages,
+                     const int *stage_slots,
+                     const double *weights,
+                     int new_slot,
+                     double tau,
+                     double tau_max,
+                     double *tau_out)
+{
+  return guarded([&] {
+    *tau_out = static_cast<SimBase *>(s)->hyp_step(
+        old_slot, stages, stage_slots, weights, new_slot, tau, tau_max);
+  });
+}
+int orc_sim_ti_step(void *s, double t, double t_final, double *tau_out)
+{
+  return guarded([&] { *tau_out = static_cast<SimBase *>(s)->ti_step(t, t_final); });
+}
+int orc_sim_set_cfl(void *s, double cfl)
+{
+  return guarded([&] { static_cast<SimBase *>(s)->set_cfl(cfl); });
+}
+int orc_sim_set_strategy(void *s, int raise)
+{
+  return guarded([&] { static_cast<SimBase *>(s)->set_strategy(raise); });
+}
+int orc_sim_configure_ti(void *s, int scheme, double cfl_min, double cfl_max, int recovery)
+{
+  return guarded([&] {
+    static_cast<SimBase *>(s)->configure_ti(scheme, cfl_min, cfl_max, recovery);
+  });
+}
+int orc_sim_get_scratch(void *s, int what, double *out)
+{
+  return guarded([&] { static_cast<SimBase *>(s)->get_scratch(what, out); });
+}
+int orc_sim_counters(void *s, unsigned int *restarts, unsigned int *warnings)
+{
+  return guarded([&] { static_cast<SimBase *>(s)->counters(restarts, warnings); });
+}
+double orc_sim_last_tau_max(void *s) { return static_cast<SimBase *>(s)->last_tau_max(); }
+int orc_sim_errors(void *s, double t, double *out3)
+{
+  return guarded([&] { static_cast<SimBase *>(s)->errors(t, out3); });
+}
+
+} /* extern "C" */

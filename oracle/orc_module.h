@@ -1,0 +1,612 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see orc_common.h).
+//
+// Restatement of the explicit hyperbolic update:
+//   prepare_state_vector  <- source/hyperbolic_module.template.h:97-193
+//   step<stages>          <- source/hyperbolic_module.template.h:236-1211
+// in the reference's *scalar* (non-SIMD) row semantics on a plain CSR stencil
+// with "diagonal first, then ascending column" row ordering
+// (tests/common/sparse_matrix_simd.output).
+#pragma once
+
+#include "orc_common.h"
+
+#include <atomic>
+#include <functional>
+#include <stdexcept>
+
+namespace orc
+{
+  /* Thrown on an invariant-domain violation when the strategy is
+   * raise_exception; hyperbolic_module.h:37-61. */
+  struct Restart {
+  };
+
+  enum class IDViolationStrategy { warn, raise_exception };
+
+  template <int dim>
+  struct BoundaryDescription { /* offline_data.h:66-72 */
+    unsigned int i;
+    Vec<dim> normal;
+    double normal_mass;
+    double boundary_mass;
+    int id;
+    Vec<dim> position;
+  };
+
+  struct CouplingDescription { /* offline_data.h:78-80 */
+    unsigned int i, col_idx, j;
+  };
+
+  /* Host view of what OfflineData hands to the module (offline_data.h:109-264),
+   * single rank, local numbering == global numbering. */
+  template <int dim>
+  struct OfflineData {
+    unsigned int n_owned = 0;
+    std::vector<unsigned int> row_ptr;    /* n_owned + 1 */
+    std::vector<unsigned int> cols;       /* nnz, diag first then ascending */
+    std::vector<unsigned int> transposed; /* nnz: flat index of (j,i) */
+    std::vector<double> mij;              /* nnz */
+    std::vector<double> cij;              /* nnz * dim, entry-major */
+    std::vector<double> mi, mi_inv;       /* n_owned */
+    double measure_of_omega = 0.;
+    std::vector<BoundaryDescription<dim>> boundary_map;
+    std::vector<CouplingDescription> coupling_boundary_pairs;
+
+    unsigned int row_length(unsigned int i) const
+    {
+      return row_ptr[i + 1] - row_ptr[i];
+    }
+
+    Vec<dim> c(std::size_t e) const
+    {
+      Vec<dim> r;
+      for (int d = 0; d < dim; ++d)
+        r[d] = cij[e * dim + d];
+      return r;
+    }
+
+    void build_transposed()
+    {
+      transposed.assign(cols.size(), 0u);
+      for (unsigned int i = 0; i < n_owned; ++i)
+        for (unsigned int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+          const unsigned int j = cols[e];
+          bool found = false;
+          for (unsigned int f = row_ptr[j]; f < row_ptr[j + 1]; ++f)
+            if (cols[f] == i) {
+              transposed[e] = f;
+              found = true;
+              break;
+            }
+          if (!found)
+            throw std::runtime_error("oracle: stencil is not symmetric");
+        }
+    }
+  };
+
+
+  /* Description concept (source/euler/description.h:31-50), reduced to what
+   * the hyperbolic update needs. */
+  template <typename SystemT,
+            typename RiemannSolverT,
+            typename IndicatorT,
+            typename LimiterT>
+  struct Description {
+    using System = SystemT;
+    using RiemannSolver = RiemannSolverT;
+    using Indicator = IndicatorT;
+    using Limiter = LimiterT;
+  };
+
+
+  template <typename Desc, int dim>
+  class HyperbolicModule
+  {
+  public:
+    using System = typename Desc::System;
+    using state_type = typename System::state_type;
+    using precomputed_type = typename System::precomputed_type;
+    using bounds_type = typename System::bounds_type;
+    static constexpr int k = System::k;
+    static constexpr int n_prec = System::n_precomputed;
+    static constexpr int n_bounds = System::n_bounds;
+
+    /* StateVector = (U, precomputed); AoS like MultiComponentVector
+     * (multicomponent_vector.h:266): (U_i)_c at i*k + c. */
+    struct StateVector {
+      std::vector<double> U;
+      std::vector<double> prec;
+      void reinit(unsigned int n)
+      {
+        U.assign(std::size_t(n) * k, 0.);
+        prec.assign(std::size_t(n) * n_prec, 0.);
+      }
+      void swap(StateVector &o)
+      {
+        U.swap(o.U);
+        prec.swap(o.prec);
+      }
+    };
+
+    using DirichletFunction =
+        std::function<state_type(const Vec<dim> &, double)>;
+
+    HyperbolicModule(const OfflineData<dim> &od,
+                     const System &sys,
+                     DirichletFunction initial_state)
+        : id_violation_strategy_(IDViolationStrategy::warn)
+        , od_(od)
+        , sys_(sys)
+        , initial_state_(std::move(initial_state))
+        , cfl_(0.2)
+        , n_restarts_(0)
+        , n_warnings_(0)
+    {
+    }
+
+    void prepare()
+    {
+      if (sys_.prm.limiter_iterations > 2)
+        throw std::runtime_error(
+            "The number of limiter iterations must be between [0,2]");
+      const std::size_t n = od_.n_owned, nnz = od_.cols.size();
+      alpha_.assign(n, 0.);
+      bounds_.assign(n * n_bounds, 0.);
+      r_.assign(n * k, 0.);
+      dij_.assign(nnz, 0.);
+      lij_.assign(nnz, 0.);
+      lij_next_.assign(nnz, 0.);
+      pij_.assign(nnz * k, 0.);
+    }
+
+    static state_type get(const std::vector<double> &v, std::size_t i)
+    {
+      state_type s;
+      for (int c = 0; c < k; ++c)
+        s[c] = v[i * k + c];
+      return s;
+    }
+
+    static void put(std::vector<double> &v, std::size_t i, const state_type &s)
+    {
+      for (int c = 0; c < k; ++c)
+        v[i * k + c] = s[c];
+    }
+
+    static precomputed_type getp(const std::vector<double> &v, std::size_t i)
+    {
+      precomputed_type s;
+      for (int c = 0; c < n_prec; ++c)
+        s[c] = v[i * n_prec + c];
+      return s;
+    }
+
+    /* hyperbolic_module.template.h:97-193 */
+    void prepare_state_vector(StateVector &sv, double t) const
+    {
+      for (const auto &entry : od_.boundary_map) {
+        if (entry.id == Boundary::do_nothing)
+          continue;
+        auto U_i = get(sv.U, entry.i);
+        auto get_dirichlet_data = [&]() {
+          return initial_state_(entry.position, t);
+        };
+        U_i = sys_.apply_boundary_conditions(
+            entry.id, U_i, entry.normal, get_dirichlet_data);
+        put(sv.U, entry.i, U_i);
+      }
+
+      const unsigned int n = od_.n_owned;
+#pragma omp parallel for schedule(static)
+      for (unsigned int i = 0; i < n; ++i) {
+        if (od_.row_length(i) == 1)
+          continue;
+        const auto U_i = get(sv.U, i);
+        const auto prec_i = sys_.precompute(U_i);
+        for (int c = 0; c < n_prec; ++c)
+          sv.prec[std::size_t(i) * n_prec + c] = prec_i[c];
+      }
+    }
+
+    /* hyperbolic_module.template.h:236-1211; stage vectors passed as
+     * pointers, stages = stage_U.size(). */
+    double step(const StateVector &old_sv,
+                const std::vector<const StateVector *> &stage_sv,
+                const std::vector<double> &stage_weights,
+                StateVector &new_sv,
+                double tau = 0.,
+                double tau_max_in = max_double) const
+    {
+      using RiemannSolver = typename Desc::RiemannSolver;
+      using Indicator = typename Desc::Indicator;
+      using Limiter = typename Desc::Limiter;
+
+      const int stages = int(stage_sv.size());
+      const auto &old_U = old_sv.U;
+      const auto &old_prec = old_sv.prec;
+      auto &new_U = new_sv.U;
+
+      const unsigned int n_owned = od_.n_owned;
+      const double measure_of_omega_inverse = 1. / od_.measure_of_omega;
+
+      bool restart_needed = false;
+
+      /* Step 2: off-diagonal d_ij (upper triangle), alpha_i; :341-424 */
+#pragma omp parallel
+      {
+        RiemannSolver riemann_solver(sys_);
+        Indicator indicator(sys_);
+#pragma omp for schedule(static)
+        for (unsigned int i = 0; i < n_owned; ++i) {
+          const unsigned int row_length = od_.row_length(i);
+          if (row_length == 1)
+            continue;
+          const auto U_i = get(old_U, i);
+          indicator.reset(getp(old_prec, i), U_i);
+
+          const std::size_t e0 = od_.row_ptr[i];
+          for (unsigned int col_idx = 0; col_idx < row_length; ++col_idx) {
+            const std::size_t e = e0 + col_idx;
+            const unsigned int j = od_.cols[e];
+            const auto U_j = get(old_U, j);
+            const auto c_ij = od_.c(e);
+
+            indicator.accumulate(getp(old_prec, j), U_j, c_ij);
+
+            if (col_idx == 0)
+              continue;
+            if (j < i)
+              continue;
+
+            const double nrm = norm<dim>(c_ij);
+            Vec<dim> n_ij;
+            for (int d = 0; d < dim; ++d)
+              n_ij[d] = c_ij[d] / nrm;
+            const double lambda_max = riemann_solver.compute(U_i, U_j, n_ij);
+            dij_[e] = nrm * lambda_max;
+          }
+
+          const double hd_i = od_.mi[i] * measure_of_omega_inverse;
+          alpha_[i] = indicator.alpha(hd_i);
+        }
+      }
+
+      /* Step 3: boundary d_ij, symmetrize, diagonal, tau_max; :432-564 */
+      double tau_max = tau_max_in;
+      {
+        RiemannSolver riemann_solver(sys_);
+        for (const auto &cp : od_.coupling_boundary_pairs) {
+          const unsigned int i = cp.i, col_idx = cp.col_idx, j = cp.j;
+          if (j < i)
+            continue;
+          const auto U_i = get(old_U, i);
+          const auto U_j = get(old_U, j);
+          const std::size_t e = od_.row_ptr[i] + col_idx;
+          const auto c_ji = od_.c(od_.transposed[e]);
+          const double norm_ji = norm<dim>(c_ji);
+          Vec<dim> n_ji;
+          for (int d = 0; d < dim; ++d)
+            n_ji[d] = c_ji[d] / norm_ji;
+          const double d_ij = dij_[e];
+          const double lambda_max = riemann_solver.compute(U_j, U_i, n_ji);
+          const double d_ji = norm_ji * lambda_max;
+          dij_[e] = std::max(d_ij, d_ji);
+        }
+
+        double local_tau_max = max_double;
+        /* the lower-triangular fill reads upper-triangular entries only, so
+         * rows are independent: */
+#pragma omp parallel for schedule(static) reduction(min : local_tau_max)
+        for (unsigned int i = 0; i < n_owned; ++i) {
+          const unsigned int row_length = od_.row_length(i);
+          if (row_length == 1)
+            continue;
+          double d_sum = 0.;
+          const std::size_t e0 = od_.row_ptr[i];
+          for (unsigned int col_idx = 1; col_idx < row_length; ++col_idx) {
+            const std::size_t e = e0 + col_idx;
+            const unsigned int j = od_.cols[e];
+            if (j < i)
+              dij_[e] = dij_[od_.transposed[e]];
+            d_sum -= dij_[e];
+          }
+          d_sum = std::min(d_sum, -1.e6 * min_double);
+          dij_[e0] = d_sum;
+          const double mass = od_.mi[i];
+          const double tau_i = cfl_ * mass / (-2. * d_sum);
+          local_tau_max = std::min(local_tau_max, tau_i);
+        }
+        tau_max = std::min(tau_max, local_tau_max);
+      }
+
+      if (std::isnan(tau_max) || std::isinf(tau_max) || !(tau_max > 0.))
+        throw std::runtime_error(
+            "I'm sorry, Dave. I'm afraid I can't do that.\nWe crashed.");
+
+      tau = (tau == 0. ? tau_max : tau);
+      last_tau_max_ = tau_max;
+
+      /* Step 4: low-order update, bounds, r_i, p_ij; :597-884 */
+      {
+        double weight = 1.;
+        {
+          /* -std::accumulate(w.begin(), w.end(), -1.) */
+          double acc = -1.;
+          for (double w : stage_weights)
+            acc += w;
+          weight = -acc;
+        }
+
+#pragma omp parallel
+        {
+          Limiter limiter(sys_);
+#pragma omp for schedule(static)
+          for (unsigned int i = 0; i < n_owned; ++i) {
+            const unsigned int row_length = od_.row_length(i);
+            if (row_length == 1)
+              continue;
+
+            const auto U_i = get(old_U, i);
+            auto U_i_new = U_i;
+
+            const double alpha_i = alpha_[i];
+            const double m_i = od_.mi[i];
+            const double m_i_inv = od_.mi_inv[i];
+
+            const auto flux_i = sys_.f(U_i);
+            std::vector<typename System::flux_type> flux_iHs(stages);
+            for (int s = 0; s < stages; ++s)
+              flux_iHs[s] = sys_.f(get(stage_sv[s]->U, i));
+
+            state_type F_iH;
+            F_iH.fill(0.);
+
+            limiter.reset(U_i);
+
+            const std::size_t e0 = od_.row_ptr[i];
+            for (unsigned int col_idx = 0; col_idx < row_length; ++col_idx) {
+              const std::size_t e = e0 + col_idx;
+              const unsigned int j = od_.cols[e];
+
+              const auto U_j = get(old_U, j);
+              const double alpha_j = alpha_[j];
+
+              const double d_ij = dij_[e];
+              const double factor = (alpha_i + alpha_j) * .5;
+              const double d_ijH = d_ij * factor;
+
+              const auto c_ij = od_.c(e);
+              const double regularization = 100. * min_double;
+              Vec<dim> scaled_c_ij;
+              {
+                const double div = std::max(d_ij, regularization);
+                for (int d = 0; d < dim; ++d)
+                  scaled_c_ij[d] = c_ij[d] / div;
+              }
+
+              const auto flux_j = sys_.f(U_j);
+
+              const auto flux_ij =
+                  System::flux_divergence(flux_i, flux_j, c_ij);
+              state_type P_ij;
+              for (int c = 0; c < k; ++c) {
+                U_i_new[c] += tau * m_i_inv * flux_ij[c];
+                P_ij[c] = -flux_ij[c];
+              }
+
+              for (int c = 0; c < k; ++c) {
+                const double diff = U_j[c] - U_i[c];
+                U_i_new[c] += tau * m_i_inv * d_ij * diff;
+                F_iH[c] += d_ijH * diff;
+                P_ij[c] += (d_ijH - d_ij) * diff;
+              }
+
+              limiter.accumulate(getp(old_prec, j), U_j, scaled_c_ij);
+
+              for (int c = 0; c < k; ++c) {
+                F_iH[c] += weight * flux_ij[c];
+                P_ij[c] += weight * flux_ij[c];
+              }
+
+              for (int s = 0; s < stages; ++s) {
+                const auto U_jHs = get(stage_sv[s]->U, j);
+                const auto flux_jHs = sys_.f(U_jHs);
+                const auto flux_ij_s =
+                    System::flux_divergence(flux_iHs[s], flux_jHs, c_ij);
+                for (int c = 0; c < k; ++c) {
+                  F_iH[c] += stage_weights[s] * flux_ij_s[c];
+                  P_ij[c] += stage_weights[s] * flux_ij_s[c];
+                }
+              }
+
+              for (int c = 0; c < k; ++c)
+                pij_[e * k + c] = P_ij[c];
+            }
+
+            if (sys_.prm.expensive_bounds_check && !sys_.is_admissible(U_i_new)) {
+#pragma omp atomic write
+              restart_needed = true;
+            }
+
+            put(new_U, i, U_i_new);
+            put(r_, i, F_iH);
+
+            const double hd_i = m_i * measure_of_omega_inverse;
+            const auto relaxed_bounds = limiter.bounds(hd_i);
+            for (int b = 0; b < n_bounds; ++b)
+              bounds_[std::size_t(i) * n_bounds + b] = relaxed_bounds[b];
+          }
+        }
+      }
+
+      /* Step 5: second part of p_ij, first l_ij; :892-1041 */
+      if (sys_.prm.limiter_iterations != 0) {
+#pragma omp parallel
+        {
+          Limiter limiter(sys_);
+#pragma omp for schedule(static)
+          for (unsigned int i = 0; i < n_owned; ++i) {
+            const unsigned int row_length = od_.row_length(i);
+            if (row_length == 1)
+              continue;
+
+            bounds_type bounds;
+            for (int b = 0; b < n_bounds; ++b)
+              bounds[b] = bounds_[std::size_t(i) * n_bounds + b];
+
+            const double m_i_inv = od_.mi_inv[i];
+            const auto U_i_new = get(new_U, i);
+            const auto F_iH = get(r_, i);
+
+            const double lambda_inv = double(row_length - 1);
+            const double factor = tau * m_i_inv * lambda_inv;
+
+            const std::size_t e0 = od_.row_ptr[i];
+            for (unsigned int col_idx = 1; col_idx < row_length; ++col_idx) {
+              const std::size_t e = e0 + col_idx;
+              const unsigned int j = od_.cols[e];
+
+              state_type P_ij;
+              for (int c = 0; c < k; ++c)
+                P_ij[c] = pij_[e * k + c];
+              const auto F_jH = get(r_, j);
+
+              const double kronecker_ij = col_idx == 0 ? 1. : 0.;
+              const double m_j_inv = od_.mi_inv[j];
+              const double m_ij = od_.mij[e];
+              const double b_ij = kronecker_ij - m_ij * m_j_inv;
+              const double b_ji = kronecker_ij - m_ij * m_i_inv;
+
+              for (int c = 0; c < k; ++c) {
+                P_ij[c] += b_ij * F_jH[c] - b_ji * F_iH[c];
+                P_ij[c] *= factor;
+                pij_[e * k + c] = P_ij[c];
+              }
+
+              bool success;
+              const double l_ij = limiter.limit(bounds, U_i_new, P_ij, success);
+              lij_[e] = l_ij;
+
+              if (!success) {
+#pragma omp atomic write
+                restart_needed = true;
+              }
+            }
+          }
+        }
+      }
+
+      /* Steps 6, 7: symmetrize l_ij, high-order update, next l_ij;
+       * :1053-1182 */
+      const unsigned int n_iterations = sys_.prm.limiter_iterations;
+      for (unsigned int pass = 0; pass < n_iterations; ++pass) {
+        const bool last_round = (pass + 1 == n_iterations);
+
+        if ((n_iterations == 2) && last_round)
+          std::swap(lij_, lij_next_);
+
+#pragma omp parallel
+        {
+          Limiter limiter(sys_);
+          std::vector<double> lij_row;
+#pragma omp for schedule(static)
+          for (unsigned int i = 0; i < n_owned; ++i) {
+            const unsigned int row_length = od_.row_length(i);
+            if (row_length == 1)
+              continue;
+
+            auto U_i_new = get(new_U, i);
+            const double lambda = 1. / double(row_length - 1);
+            lij_row.resize(row_length);
+
+            const std::size_t e0 = od_.row_ptr[i];
+            for (unsigned int col_idx = 1; col_idx < row_length; ++col_idx) {
+              const std::size_t e = e0 + col_idx;
+              const double l_ij = std::min(lij_[e], lij_[od_.transposed[e]]);
+              for (int c = 0; c < k; ++c)
+                U_i_new[c] += l_ij * lambda * pij_[e * k + c];
+              if (!last_round)
+                lij_row[col_idx] = l_ij;
+            }
+
+            if (sys_.prm.expensive_bounds_check && !sys_.is_admissible(U_i_new)) {
+#pragma omp atomic write
+              restart_needed = true;
+            }
+
+            put(new_U, i, U_i_new);
+
+            if (last_round)
+              continue;
+
+            bounds_type bounds;
+            for (int b = 0; b < n_bounds; ++b)
+              bounds[b] = bounds_[std::size_t(i) * n_bounds + b];
+
+            for (unsigned int col_idx = 1; col_idx < row_length; ++col_idx) {
+              const std::size_t e = e0 + col_idx;
+              const double old_l_ij = lij_row[col_idx];
+              state_type new_p_ij;
+              for (int c = 0; c < k; ++c)
+                new_p_ij[c] = (1. - old_l_ij) * pij_[e * k + c];
+
+              bool success;
+              const double new_l_ij =
+                  limiter.limit(bounds, U_i_new, new_p_ij, success);
+              if (sys_.prm.expensive_bounds_check && !success) {
+#pragma omp atomic write
+                restart_needed = true;
+              }
+              lij_next_[e] = (1. - old_l_ij) * new_l_ij;
+            }
+          }
+        }
+      }
+
+      /* :1190-1210 */
+      if (restart_needed) {
+        switch (id_violation_strategy_) {
+        case IDViolationStrategy::warn:
+          n_warnings_++;
+          break;
+        case IDViolationStrategy::raise_exception:
+          n_restarts_++;
+          throw Restart();
+        }
+      }
+
+      return tau;
+    }
+
+    void cfl(double new_cfl) const { cfl_ = new_cfl; }
+    double cfl() const { return cfl_; }
+    const std::vector<double> &alpha() const { return alpha_; }
+    const std::vector<double> &dij() const { return dij_; }
+    const std::vector<double> &lij() const { return lij_; }
+    const std::vector<double> &lij_next() const { return lij_next_; }
+    const std::vector<double> &pij() const { return pij_; }
+    const std::vector<double> &r() const { return r_; }
+    const std::vector<double> &bounds() const { return bounds_; }
+    unsigned int n_restarts() const { return n_restarts_; }
+    unsigned int n_warnings() const { return n_warnings_; }
+    double last_tau_max() const { return last_tau_max_; }
+
+    mutable IDViolationStrategy id_violation_strategy_;
+
+    const OfflineData<dim> &offline_data() const { return od_; }
+    const System &system() const { return sys_; }
+    const DirichletFunction &initial_state() const { return initial_state_; }
+
+  private:
+    const OfflineData<dim> &od_;
+    const System &sys_;
+    DirichletFunction initial_state_;
+
+    mutable double cfl_;
+    mutable unsigned int n_restarts_, n_warnings_;
+    mutable double last_tau_max_ = 0.;
+
+    mutable std::vector<double> alpha_, bounds_, r_;
+    mutable std::vector<double> dij_, lij_, lij_next_, pij_;
+  };
+} // namespace orc

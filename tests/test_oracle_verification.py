@@ -1,0 +1,41 @@
+"""End-to-end pin of the oracle: the reference's isentropic-vortex verification runs
+(tests/euler/verification-isentropic_vortex-2d-{erk33,ssprk33}-l{5,6}.{prm,output}).
+
+The mesh is reproducible (uniform Q1 on [-5,5]^2) but not deal.II's DoF numbering,
+so summation order differs: agreement is expected at ~1e-10 relative (the reference's
+own mpirun=4 vs mpirun=8 goldens differ at that level), not bitwise.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import orc
+
+
+def run_vortex(oracle, refinement, scheme):
+    n = 2**refinement
+    off = oracle.assemble([n, n], [-5.0, -5.0], [10.0 / n, 10.0 / n], [orc.DIRICHLET] * 4)
+    sim = off.euler_sim(kind=orc.ISENTROPIC_VORTEX, direction=(1.0, 1.0), position=(-1.0, -1.0), mach=1.0, beta=5.0, gamma=1.4)
+    sim.configure_time_integrator(scheme=scheme, cfl_min=0.2, cfl_max=0.2, recovery="none")
+    sim.interpolate(0.0)
+    t, t_final = 0.0, 2.0
+    cycles = 0
+    while t < t_final:  # time_loop.template.h:357 (final time not enforced)
+        t += sim.time_step(t)
+        cycles += 1
+    return off, sim, t, cycles
+
+
+@pytest.mark.parametrize("scheme,key", [("erk 33", "erk33"), ("ssprk 33", "ssprk33")])
+@pytest.mark.parametrize("refinement", [5, 6, 7])
+def test_isentropic_vortex_verification(oracle, scheme, key, refinement):
+    g = load_golden("euler_verification.json")
+    ref = [r for r in g["runs"] if r["scheme"] == key and r["refinement"] == refinement][0]
+    off, sim, t, cycles = run_vortex(oracle, refinement, scheme)
+    assert off.n == ref["dofs"]
+    err = sim.errors(t)
+    # final time depends on every tau_max, i.e. on every d_ij of every step
+    assert abs(t - ref["t"]) <= 4e-15 * ref["t"], (t, ref["t"])
+    for name in ("Linf", "L1", "L2"):
+        assert abs(err[name] - ref[name]) <= (1e-10 if refinement == 7 else 1e-11) * ref[name], (name, err[name], ref[name])
+    assert sim.counters() == (0, 0)
