@@ -1,0 +1,90 @@
+// Shared device helpers.
+//   positive_part / negative_part  <- source/simd.h:112-127
+//   quadratic_newton_step          <- source/newton.h:39-101
+#pragma once
+
+#include "../../include/ryujin_b200.h"
+
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <stdexcept>
+#include <string>
+
+#define RJ_DEVICE __device__ __forceinline__
+
+namespace rjb
+{
+  constexpr int warp_size = 32; /* slice height C of the sliced-ELL layout */
+
+  RJ_DEVICE double positive_part(const double x)
+  {
+    return 0.5 * (fabs(x) + x);
+  }
+
+  RJ_DEVICE double negative_part(const double x)
+  {
+    return 0.5 * (fabs(x) - x);
+  }
+
+  RJ_DEVICE void quadratic_newton_step(double &p_1,
+                                       double &p_2,
+                                       const double phi_p_1,
+                                       const double phi_p_2,
+                                       const double dphi_p_1,
+                                       const double dphi_p_2,
+                                       const double sign)
+  {
+    const double scaling = 1. / (p_2 - p_1 + DBL_EPSILON);
+
+    const double dd_11 = dphi_p_1;
+    const double dd_12 = (phi_p_2 - phi_p_1) * scaling;
+    const double dd_22 = dphi_p_2;
+
+    const double dd_112 = (dd_12 - dd_11) * scaling;
+    const double dd_122 = (dd_22 - dd_12) * scaling;
+
+    const double discriminant_1 = fabs(dphi_p_1 * dphi_p_1 - 4. * phi_p_1 * dd_112);
+    const double discriminant_2 = fabs(dphi_p_2 * dphi_p_2 - 4. * phi_p_2 * dd_122);
+
+    const double denominator_1 = dphi_p_1 + sign * sqrt(discriminant_1);
+    const double denominator_2 = dphi_p_2 + sign * sqrt(discriminant_2);
+
+    double t_1 = p_1 - (fabs(denominator_1) < DBL_EPSILON ? 0. : 2. * phi_p_1 / denominator_1);
+    double t_2 = p_2 - (fabs(denominator_2) < DBL_EPSILON ? 0. : 2. * phi_p_2 / denominator_2);
+
+    t_1 = fmax(p_1, t_1);
+    t_1 = fmin(p_2, t_1);
+    t_2 = fmax(p_1, t_2);
+    t_2 = fmin(p_2, t_2);
+
+    p_1 = fmin(t_1, t_2);
+    p_2 = fmax(t_1, t_2);
+  }
+
+  /* host side error plumbing */
+  struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+  };
+  struct NcclError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+  };
+  struct InvalidArgument : std::runtime_error {
+    using std::runtime_error::runtime_error;
+  };
+  struct NumericError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+  };
+  struct NoDevice : std::runtime_error {
+    using std::runtime_error::runtime_error;
+  };
+
+  inline void cuda_check(cudaError_t err, const char *what, const char *file, int line)
+  {
+    if (err != cudaSuccess)
+      throw CudaError(std::string(what) + " failed: " + cudaGetErrorString(err) + " (" + file +
+                      ":" + std::to_string(line) + ")");
+  }
+} // namespace rjb
+
+#define RJ_CUDA(expr) ::rjb::cuda_check((expr), #expr, __FILE__, __LINE__)

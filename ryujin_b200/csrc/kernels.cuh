@@ -1,0 +1,675 @@
+// The sweep kernels of the explicit hyperbolic update, one per loop of
+// HyperbolicModule::step() (source/hyperbolic_module.template.h:236-1211) and
+// prepare_state_vector() (:97-193).  Templated on the equation module Eq
+// (euler.cuh, shallow_water.cuh): the same plug-in surface as the reference's
+// Description (HyperbolicSystemView / RiemannSolver / Indicator / Limiter).
+//
+// Mapping: one thread per stencil row; lane l of a warp owns row 32 g + l of
+// slice g, so all matrix loads (c_ij, m_ij, d_ij, l_ij, P_ij, column indices)
+// are coalesced 128/256 byte lines, and neighbour gathers U_j are contiguous
+// whenever the DoF ordering keeps neighbours of consecutive rows consecutive.
+// Per-row accumulations stay in one thread in column order, exactly as the
+// reference's scalar loop; warp shuffles are only used for the CFL minimum.
+// No tensor cores: the per-edge work is k = dim+2 component FP64 algebra.
+#pragma once
+
+#include "device_common.cuh"
+
+namespace rjb
+{
+  struct StencilView {
+    uint32_t n_owned, ld, E_owned;
+    const uint32_t *__restrict__ slice_offsets;
+    const uint8_t *__restrict__ row_length;
+    const uint32_t *__restrict__ cols;
+    const uint32_t *__restrict__ transposed;
+    const double *__restrict__ mij;
+    const double *__restrict__ cij;
+    const double *__restrict__ mi;
+    const double *__restrict__ mi_inv;
+    double measure_of_omega_inverse;
+  };
+
+  /* device scalars of one step() */
+  struct StepScalars {
+    unsigned long long tau_max_bits; /* min over rows, ordered-bits of a positive double */
+    double tau_max;                  /* after min with caller's tau_max (and all-reduce) */
+    double tau;                      /* time step used by the update kernels */
+    int restart_needed;
+    int numeric_error;
+  };
+
+  template <int n>
+  struct StagePointers {
+    const double *U[n > 0 ? n : 1];
+    const double *prec[n > 0 ? n : 1];
+    double weight[n > 0 ? n : 1];
+  };
+
+  template <int k>
+  RJ_DEVICE void load_state(const double *__restrict__ v, uint32_t ld, uint32_t i, double (&out)[k])
+  {
+#pragma unroll
+    for (int q = 0; q < k; ++q)
+      out[q] = v[size_t(q) * ld + i];
+  }
+
+  template <int k>
+  RJ_DEVICE void store_state(double *__restrict__ v, uint32_t ld, uint32_t i, const double (&in)[k])
+  {
+#pragma unroll
+    for (int q = 0; q < k; ++q)
+      v[size_t(q) * ld + i] = in[q];
+  }
+
+  /* common row prologue: returns false if the thread has no row to work on */
+  struct RowInfo {
+    uint32_t i, len, width, base;
+  };
+
+  RJ_DEVICE bool row_info(const StencilView &v, uint32_t row_begin, uint32_t row_end, RowInfo &r)
+  {
+    r.i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r.i >= row_end)
+      return false;
+    const uint32_t g = r.i >> 5;
+    const uint32_t s0 = v.slice_offsets[g];
+    r.width = (v.slice_offsets[g + 1] - s0) >> 5;
+    r.base = s0 + (r.i & 31u);
+    r.len = v.row_length[r.i];
+    return true;
+  }
+
+
+  /* ---------------------------------------------------------------------- *
+   * Step 1a: boundary conditions, hyperbolic_module.template.h:122-144.
+   * One thread per boundary DoF; entries of a DoF are applied in stored order.
+   * ---------------------------------------------------------------------- */
+  template <class Eq, class IV>
+  __global__ void k_apply_boundary_conditions(uint32_t n_groups,
+                                              const uint32_t *__restrict__ group_dof,
+                                              const uint32_t *__restrict__ group_start,
+                                              const double *__restrict__ bnormal,
+                                              const double *__restrict__ bposition,
+                                              const int32_t *__restrict__ bid,
+                                              uint32_t ld,
+                                              typename Eq::Params prm,
+                                              IV iv,
+                                              double t,
+                                              double *__restrict__ U)
+  {
+    constexpr int k = Eq::k, dim = Eq::dim;
+    const uint32_t gidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gidx >= n_groups)
+      return;
+    const uint32_t i = group_dof[gidx];
+    double U_i[k];
+    load_state<k>(U, ld, i, U_i);
+    for (uint32_t b = group_start[gidx]; b < group_start[gidx + 1]; ++b) {
+      const int id = bid[b];
+      if (id == RJ_BOUNDARY_DO_NOTHING)
+        continue;
+      double normal[dim], position[dim];
+#pragma unroll
+      for (int d = 0; d < dim; ++d) {
+        normal[d] = bnormal[size_t(b) * dim + d];
+        position[d] = bposition[size_t(b) * dim + d];
+      }
+      Eq::apply_boundary_conditions(
+          prm, id, U_i, normal, [&](double(&D)[k]) { iv.template initial_state<Eq>(prm, position, t, D); });
+    }
+    store_state<k>(U, ld, i, U_i);
+  }
+
+
+  /* U <- initial_state(x_i, t): InitialValues::interpolate_hyperbolic_vector */
+  template <class Eq, class IV>
+  __global__ void k_interpolate(uint32_t n_owned,
+                                uint32_t ld,
+                                const double *__restrict__ positions,
+                                typename Eq::Params prm,
+                                IV iv,
+                                double t,
+                                double *__restrict__ U)
+  {
+    constexpr int k = Eq::k, dim = Eq::dim;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_owned)
+      return;
+    double x[dim];
+#pragma unroll
+    for (int d = 0; d < dim; ++d)
+      x[d] = positions[size_t(d) * n_owned + i];
+    double U_i[k];
+    iv.template initial_state<Eq>(prm, x, t, U_i);
+    store_state<k>(U, ld, i, U_i);
+  }
+
+
+  /* ---------------------------------------------------------------------- *
+   * Step 1b: precomputed values, hyperbolic_module.template.h:154-192 and
+   * euler/hyperbolic_system.h:705-737.
+   * ---------------------------------------------------------------------- */
+  template <class Eq>
+  __global__ void k_precompute(StencilView v,
+                               typename Eq::Params prm,
+                               uint32_t row_begin,
+                               uint32_t row_end,
+                               const double *__restrict__ U,
+                               double *__restrict__ prec)
+  {
+    constexpr int k = Eq::k, np = Eq::n_prec;
+    RowInfo r;
+    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+      return;
+    double U_i[k], prec_i[np];
+    load_state<k>(U, v.ld, r.i, U_i);
+    Eq::precompute(prm, U_i, prec_i);
+    store_state<np>(prec, v.ld, r.i, prec_i);
+  }
+
+
+  /* ---------------------------------------------------------------------- *
+   * Step 2: off-diagonal d_ij for j > i and alpha_i,
+   * hyperbolic_module.template.h:341-424.  Additionally mirrors d_ij into the
+   * transposed slot (j, i), which replaces the gather of step 3 (:511-535).
+   * ---------------------------------------------------------------------- */
+  template <class Eq>
+  __global__ void __launch_bounds__(128) k_dij_alpha(StencilView v,
+                                                     typename Eq::Params prm,
+                                                     uint32_t row_begin,
+                                                     uint32_t row_end,
+                                                     const double *__restrict__ U,
+                                                     const double *__restrict__ prec,
+                                                     double *__restrict__ dij,
+                                                     double *__restrict__ alpha)
+  {
+    constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec;
+    RowInfo r;
+    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+      return;
+    const uint32_t i = r.i;
+
+    double U_i[k], prec_i[np];
+    load_state<k>(U, v.ld, i, U_i);
+    load_state<np>(prec, v.ld, i, prec_i);
+
+    typename Eq::Indicator indicator;
+    indicator.reset(prm, prec_i, U_i);
+
+    for (uint32_t col = 0; col < r.len; ++col) {
+      const uint32_t e = r.base + col * 32;
+      const uint32_t j = v.cols[e];
+      double U_j[k], prec_j[np], c_ij[dim];
+      load_state<k>(U, v.ld, j, U_j);
+      load_state<np>(prec, v.ld, j, prec_j);
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
+
+      indicator.accumulate(prm, U_i, prec_i, U_j, prec_j, c_ij);
+
+      if (col == 0 || j < i)
+        continue;
+
+      double nrm2 = c_ij[0] * c_ij[0];
+#pragma unroll
+      for (int d = 1; d < dim; ++d)
+        nrm2 += c_ij[d] * c_ij[d];
+      const double nrm = sqrt(nrm2);
+      const double inv = 1. / nrm;
+      double n_ij[dim];
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        n_ij[d] = c_ij[d] * inv;
+      const double lambda_max = Eq::riemann_lambda_max(prm, U_i, prec_i, U_j, prec_j, n_ij);
+      const double d_ij = nrm * lambda_max;
+      dij[e] = d_ij;
+      const uint32_t eT = v.transposed[e];
+      if (eT < v.E_owned)
+        dij[eT] = d_ij;
+    }
+
+    const double hd_i = v.mi[i] * v.measure_of_omega_inverse;
+    alpha[i] = indicator.alpha(prm, hd_i);
+  }
+
+
+  /* Step 3a: complete d_ij on coupling boundary pairs (i < j),
+   * hyperbolic_module.template.h:461-490. */
+  template <class Eq>
+  __global__ void k_boundary_dij(uint32_t n_pairs,
+                                 const uint32_t *__restrict__ pair_i,
+                                 const uint32_t *__restrict__ pair_j,
+                                 const uint32_t *__restrict__ pair_e,
+                                 const uint32_t *__restrict__ pair_eT,
+                                 const double *__restrict__ pair_cji,
+                                 uint32_t ld,
+                                 uint32_t E_owned,
+                                 typename Eq::Params prm,
+                                 const double *__restrict__ U,
+                                 const double *__restrict__ prec,
+                                 double *__restrict__ dij)
+  {
+    constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs)
+      return;
+    const uint32_t i = pair_i[p], j = pair_j[p], e = pair_e[p], eT = pair_eT[p];
+    double U_i[k], U_j[k], prec_i[np], prec_j[np];
+    load_state<k>(U, ld, i, U_i);
+    load_state<k>(U, ld, j, U_j);
+    load_state<np>(prec, ld, i, prec_i);
+    load_state<np>(prec, ld, j, prec_j);
+    double c_ji[dim];
+    double nrm2 = 0.;
+#pragma unroll
+    for (int d = 0; d < dim; ++d) {
+      c_ji[d] = pair_cji[size_t(p) * dim + d];
+      nrm2 += c_ji[d] * c_ji[d];
+    }
+    const double norm_ji = sqrt(nrm2);
+    const double inv = 1. / norm_ji;
+    double n_ji[dim];
+#pragma unroll
+    for (int d = 0; d < dim; ++d)
+      n_ji[d] = c_ji[d] * inv;
+    const double d_ij = dij[e];
+    const double lambda_max = Eq::riemann_lambda_max(prm, U_j, prec_j, U_i, prec_i, n_ji);
+    const double d_ji = norm_ji * lambda_max;
+    const double d = fmax(d_ij, d_ji);
+    dij[e] = d;
+    if (eT < E_owned)
+      dij[eT] = d;
+  }
+
+
+  /* Step 3b: diagonal d_ii and tau_max, hyperbolic_module.template.h:494-560.
+   * The row sum runs in column order in one thread; only the minimum over
+   * rows (order independent) uses shuffles + one atomicMin per block. */
+  __global__ void k_dii_tau(StencilView v,
+                            uint32_t row_begin,
+                            uint32_t row_end,
+                            double cfl,
+                            double *__restrict__ dij,
+                            StepScalars *__restrict__ scalars)
+  {
+    RowInfo r;
+    double tau_i = DBL_MAX;
+    if (row_info(v, row_begin, row_end, r) && r.len > 1) {
+      double d_sum = 0.;
+      for (uint32_t col = 1; col < r.len; ++col)
+        d_sum -= dij[r.base + col * 32];
+      d_sum = fmin(d_sum, -1.e6 * DBL_MIN);
+      dij[r.base] = d_sum;
+      tau_i = cfl * v.mi[r.i] / (-2. * d_sum);
+    }
+    /* NaN must survive the reduction (AssertThrow at :573-576) */
+    unsigned long long bits =
+        (tau_i != tau_i) ? 0ull : (unsigned long long)__double_as_longlong(fmax(tau_i, 0.));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, off);
+      bits = other < bits ? other : bits;
+    }
+    __shared__ unsigned long long smin[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+      smin[warp] = bits;
+    __syncthreads();
+    if (warp == 0) {
+      const int n_warps = (blockDim.x + 31) >> 5;
+      bits = lane < n_warps ? smin[lane] : ~0ull;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, off);
+        bits = other < bits ? other : bits;
+      }
+      if (lane == 0)
+        atomicMin(&scalars->tau_max_bits, bits);
+    }
+  }
+
+  __global__ void k_reset_scalars(StepScalars *s)
+  {
+    s->tau_max_bits = (unsigned long long)__double_as_longlong(DBL_MAX);
+    s->tau_max = 0.;
+    s->tau = 0.;
+    s->restart_needed = 0;
+    s->numeric_error = 0;
+  }
+
+  /* local minimum -> tau_max (before the all-reduce over ranks) */
+  __global__ void k_tau_local(StepScalars *s, double tau_max_in)
+  {
+    const double local = __longlong_as_double((long long)s->tau_max_bits);
+    /* tau_max_bits == 0 encodes NaN or a non-positive value */
+    s->tau_max = fmin(local, tau_max_in);
+  }
+
+  /* :571-578 */
+  __global__ void k_tau_finalize(StepScalars *s, double tau_in)
+  {
+    const double tau_max = s->tau_max;
+    if (isnan(tau_max) || isinf(tau_max) || !(tau_max > 0.))
+      s->numeric_error = 1;
+    s->tau = (tau_in == 0. ? tau_max : tau_in);
+  }
+
+
+  /* ---------------------------------------------------------------------- *
+   * Step 4: low-order update, limiter bounds, r_i and P_ij,
+   * hyperbolic_module.template.h:597-884.
+   * ---------------------------------------------------------------------- */
+  template <class Eq, int stages>
+  __global__ void __launch_bounds__(128) k_low_order(StencilView v,
+                                                     typename Eq::Params prm,
+                                                     uint32_t row_begin,
+                                                     uint32_t row_end,
+                                                     const double *__restrict__ U,
+                                                     const double *__restrict__ prec,
+                                                     StagePointers<stages> st,
+                                                     const double *__restrict__ alpha,
+                                                     const double *__restrict__ dij,
+                                                     const StepScalars *__restrict__ scalars,
+                                                     double *__restrict__ U_new,
+                                                     double *__restrict__ r_vec,
+                                                     double *__restrict__ bounds,
+                                                     double *__restrict__ pij)
+  {
+    constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec, nb = Eq::n_bounds;
+    RowInfo r;
+    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+      return;
+    const uint32_t i = r.i;
+    const double tau = scalars->tau;
+
+    double weight = -1.;
+#pragma unroll
+    for (int s = 0; s < stages; ++s)
+      weight += st.weight[s];
+    weight = -weight;
+
+    double U_i[k], prec_i[np];
+    load_state<k>(U, v.ld, i, U_i);
+    load_state<np>(prec, v.ld, i, prec_i);
+    const double alpha_i = alpha[i];
+    const double m_i = v.mi[i];
+    const double m_i_inv = v.mi_inv[i];
+
+    const typename Eq::Flux flux_i = Eq::flux_contribution(prm, prec_i, U_i);
+
+    double U_is[stages > 0 ? stages : 1][k];
+    typename Eq::Flux flux_is[stages > 0 ? stages : 1];
+#pragma unroll
+    for (int s = 0; s < stages; ++s) {
+      double prec_s[np];
+      load_state<k>(st.U[s], v.ld, i, U_is[s]);
+      load_state<np>(st.prec[s], v.ld, i, prec_s);
+      flux_is[s] = Eq::flux_contribution(prm, prec_s, U_is[s]);
+    }
+
+    double U_i_new[k], F_iH[k];
+#pragma unroll
+    for (int q = 0; q < k; ++q) {
+      U_i_new[q] = U_i[q];
+      F_iH[q] = 0.;
+    }
+
+    typename Eq::LimiterAccumulator limiter;
+    limiter.reset();
+
+    const double tau_m_i_inv = tau * m_i_inv;
+
+    for (uint32_t col = 0; col < r.len; ++col) {
+      const uint32_t e = r.base + col * 32;
+      const uint32_t j = v.cols[e];
+
+      double U_j[k], prec_j[np], c_ij[dim];
+      load_state<k>(U, v.ld, j, U_j);
+      load_state<np>(prec, v.ld, j, prec_j);
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
+
+      const double alpha_j = alpha[j];
+      const double d_ij = dij[e];
+      const double factor = (alpha_i + alpha_j) * .5;
+      const double d_ijH = d_ij * factor;
+
+      const double scale = 1. / fmax(d_ij, 100. * DBL_MIN);
+      double scaled_c_ij[dim];
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        scaled_c_ij[d] = c_ij[d] * scale;
+
+      const typename Eq::Flux flux_j = Eq::flux_contribution(prm, prec_j, U_j);
+
+      double flux_ij[k], P_ij[k];
+      Eq::flux_divergence(U_i, flux_i, U_j, flux_j, c_ij, flux_ij);
+#pragma unroll
+      for (int q = 0; q < k; ++q) {
+        U_i_new[q] += tau_m_i_inv * flux_ij[q];
+        P_ij[q] = -flux_ij[q];
+      }
+
+#pragma unroll
+      for (int q = 0; q < k; ++q) {
+        const double diff = U_j[q] - U_i[q];
+        U_i_new[q] += tau_m_i_inv * d_ij * diff;
+        F_iH[q] += d_ijH * diff;
+        P_ij[q] += (d_ijH - d_ij) * diff;
+      }
+
+      limiter.accumulate(prm, U_i, U_j, prec_j, scaled_c_ij);
+
+#pragma unroll
+      for (int q = 0; q < k; ++q) {
+        F_iH[q] += weight * flux_ij[q];
+        P_ij[q] += weight * flux_ij[q];
+      }
+
+#pragma unroll
+      for (int s = 0; s < stages; ++s) {
+        double U_js[k], prec_js[np], flux_ij_s[k];
+        load_state<k>(st.U[s], v.ld, j, U_js);
+        load_state<np>(st.prec[s], v.ld, j, prec_js);
+        const typename Eq::Flux flux_js = Eq::flux_contribution(prm, prec_js, U_js);
+        Eq::flux_divergence(U_is[s], flux_is[s], U_js, flux_js, c_ij, flux_ij_s);
+#pragma unroll
+        for (int q = 0; q < k; ++q) {
+          F_iH[q] += st.weight[s] * flux_ij_s[q];
+          P_ij[q] += st.weight[s] * flux_ij_s[q];
+        }
+      }
+
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        pij[size_t(q) * v.E_owned + e] = P_ij[q];
+    }
+
+    store_state<k>(U_new, v.ld, i, U_i_new);
+    store_state<k>(r_vec, v.ld, i, F_iH);
+
+    const double hd_i = m_i * v.measure_of_omega_inverse;
+    double b[nb];
+    limiter.bounds(prm, hd_i, b);
+    store_state<nb>(bounds, v.ld, i, b);
+  }
+
+
+  /* ---------------------------------------------------------------------- *
+   * Step 5: mass-matrix correction of P_ij and first l_ij,
+   * hyperbolic_module.template.h:892-1041.
+   * ---------------------------------------------------------------------- */
+  template <class Eq>
+  __global__ void __launch_bounds__(128) k_pij_lij(StencilView v,
+                                                   typename Eq::Params prm,
+                                                   uint32_t row_begin,
+                                                   uint32_t row_end,
+                                                   const double *__restrict__ U_new,
+                                                   const double *__restrict__ r_vec,
+                                                   const double *__restrict__ bounds,
+                                                   StepScalars *__restrict__ scalars,
+                                                   double *__restrict__ pij,
+                                                   double *__restrict__ lij)
+  {
+    constexpr int k = Eq::k, nb = Eq::n_bounds;
+    RowInfo r;
+    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+      return;
+    const uint32_t i = r.i;
+    const double tau = scalars->tau;
+
+    double b[nb], U_i_new[k], F_iH[k];
+    load_state<nb>(bounds, v.ld, i, b);
+    load_state<k>(U_new, v.ld, i, U_i_new);
+    load_state<k>(r_vec, v.ld, i, F_iH);
+    const double m_i_inv = v.mi_inv[i];
+
+    const double lambda_inv = double(r.len - 1);
+    const double factor = tau * m_i_inv * lambda_inv;
+
+    bool all_ok = true;
+    for (uint32_t col = 1; col < r.len; ++col) {
+      const uint32_t e = r.base + col * 32;
+      const uint32_t j = v.cols[e];
+      double P_ij[k], F_jH[k];
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        P_ij[q] = pij[size_t(q) * v.E_owned + e];
+      load_state<k>(r_vec, v.ld, j, F_jH);
+
+      const double m_j_inv = v.mi_inv[j];
+      const double m_ij = v.mij[e];
+      const double b_ij = 0. - m_ij * m_j_inv;
+      const double b_ji = 0. - m_ij * m_i_inv;
+
+#pragma unroll
+      for (int q = 0; q < k; ++q) {
+        P_ij[q] += b_ij * F_jH[q] - b_ji * F_iH[q];
+        P_ij[q] *= factor;
+        pij[size_t(q) * v.E_owned + e] = P_ij[q];
+      }
+
+      bool success;
+      const double l_ij = Eq::limit(prm, b, U_i_new, P_ij, success);
+      lij[e] = l_ij;
+      all_ok = all_ok && success;
+    }
+    if (!all_ok)
+      atomicOr(&scalars->restart_needed, 1);
+  }
+
+
+  /* ---------------------------------------------------------------------- *
+   * Steps 6, 7: symmetrize l_ij, high-order update, next l_ij,
+   * hyperbolic_module.template.h:1053-1182.
+   * ---------------------------------------------------------------------- */
+  template <class Eq, bool last_round>
+  __global__ void __launch_bounds__(128) k_high_order(StencilView v,
+                                                      typename Eq::Params prm,
+                                                      uint32_t row_begin,
+                                                      uint32_t row_end,
+                                                      const double *__restrict__ bounds,
+                                                      const double *__restrict__ pij,
+                                                      const double *__restrict__ lij,
+                                                      double *__restrict__ lij_next,
+                                                      double *__restrict__ U_new)
+  {
+    constexpr int k = Eq::k, nb = Eq::n_bounds;
+    RowInfo r;
+    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+      return;
+    const uint32_t i = r.i;
+
+    double U_i_new[k];
+    load_state<k>(U_new, v.ld, i, U_i_new);
+    const double lambda = 1. / double(r.len - 1);
+
+    for (uint32_t col = 1; col < r.len; ++col) {
+      const uint32_t e = r.base + col * 32;
+      const double l_ij = fmin(lij[e], lij[v.transposed[e]]);
+      const double ll = l_ij * lambda;
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        U_i_new[q] += ll * pij[size_t(q) * v.E_owned + e];
+    }
+    store_state<k>(U_new, v.ld, i, U_i_new);
+
+    if (last_round)
+      return;
+
+    double b[nb];
+    load_state<nb>(bounds, v.ld, i, b);
+    for (uint32_t col = 1; col < r.len; ++col) {
+      const uint32_t e = r.base + col * 32;
+      const double old_l_ij = fmin(lij[e], lij[v.transposed[e]]);
+      double new_p_ij[k];
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        new_p_ij[q] = (1. - old_l_ij) * pij[size_t(q) * v.E_owned + e];
+      bool success;
+      const double new_l_ij = Eq::limit(prm, b, U_i_new, new_p_ij, success);
+      lij_next[e] = (1. - old_l_ij) * new_l_ij;
+    }
+  }
+
+
+  /* ---------------------------------------------------------------------- *
+   * Plumbing kernels
+   * ---------------------------------------------------------------------- */
+
+  /* host AoS (i*k + c) <-> device component-major (c*ld + i) */
+  __global__ void k_aos_to_soa(uint32_t n, uint32_t k, uint32_t ld, const double *__restrict__ aos, double *__restrict__ soa)
+  {
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= size_t(n) * k)
+      return;
+    const uint32_t i = uint32_t(t / k), c = uint32_t(t % k);
+    soa[size_t(c) * ld + i] = aos[t];
+  }
+
+  __global__ void k_soa_to_aos(uint32_t n, uint32_t k, uint32_t ld, const double *__restrict__ soa, double *__restrict__ aos)
+  {
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= size_t(n) * k)
+      return;
+    const uint32_t i = uint32_t(t / k), c = uint32_t(t % k);
+    aos[t] = soa[size_t(c) * ld + i];
+  }
+
+  /* dst = s*dst + b*src, time_integrator.template.h:18-25 */
+  __global__ void k_sadd(size_t n, double s, double b, double *__restrict__ dst, const double *__restrict__ src)
+  {
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t < n)
+      dst[t] = s * dst[t] + b * src[t];
+  }
+
+  /* gather rows of a component-major vector into a contiguous send buffer
+   * laid out [component][row] per neighbour block */
+  __global__ void k_pack_rows(uint32_t n_rows, uint32_t n_comp, uint32_t ld, const uint32_t *__restrict__ rows, const double *__restrict__ v, double *__restrict__ buf)
+  {
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= size_t(n_rows) * n_comp)
+      return;
+    const uint32_t c = uint32_t(t / n_rows), s = uint32_t(t % n_rows);
+    buf[t] = v[size_t(c) * ld + rows[s]];
+  }
+
+  __global__ void k_pack_entries(uint32_t n, const uint32_t *__restrict__ entries, const double *__restrict__ m, double *__restrict__ buf)
+  {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n)
+      buf[t] = m[entries[t]];
+  }
+
+  /* CSR-ordered copy of a sliced matrix (introspection) */
+  __global__ void k_gather_entries(size_t n, const uint32_t *__restrict__ entries, const double *__restrict__ m, double *__restrict__ out)
+  {
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t < n)
+      out[t] = m[entries[t]];
+  }
+} // namespace rjb

@@ -1,0 +1,1253 @@
+// Host side of the B200 hyperbolic module: owns the device scratch, launches
+// the sweep kernels of kernels.cuh in the order of HyperbolicModule::step()
+// (source/hyperbolic_module.template.h:236-1211) and runs the ghost exchanges
+// C1-C9 of SURVEY.md section 2b over NCCL.  Also: state vectors, the
+// TimeIntegrator shim and the extern "C" surface declared in
+// include/ryujin_b200.h.
+
+#include "device_offline.h"
+#include "euler.cuh"
+#include "host_offline.h"
+#include "initial_values.cuh"
+#include "kernels.cuh"
+
+#include <nccl.h>
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+namespace rjb
+{
+  thread_local std::string g_last_error;
+
+  inline void nccl_check(ncclResult_t r, const char *what, const char *file, int line)
+  {
+    if (r != ncclSuccess)
+      throw NcclError(std::string(what) + " failed: " + ncclGetErrorString(r) + " (" + file + ":" +
+                      std::to_string(line) + ")");
+  }
+#define RJ_NCCL(expr) ::rjb::nccl_check((expr), #expr, __FILE__, __LINE__)
+
+  template <typename F>
+  int guarded(const F &f)
+  {
+    try {
+      return f();
+    } catch (const InvalidArgument &e) {
+      g_last_error = e.what();
+      return RJ_ERR_INVALID;
+    } catch (const CudaError &e) {
+      g_last_error = e.what();
+      return RJ_ERR_CUDA;
+    } catch (const NcclError &e) {
+      g_last_error = e.what();
+      return RJ_ERR_NCCL;
+    } catch (const NumericError &e) {
+      g_last_error = e.what();
+      return RJ_ERR_NUMERIC;
+    } catch (const NoDevice &e) {
+      g_last_error = e.what();
+      return RJ_ERR_NO_DEVICE;
+    } catch (const std::exception &e) {
+      g_last_error = e.what();
+      return RJ_ERR_INVALID;
+    }
+  }
+} // namespace rjb
+
+using namespace rjb;
+
+struct rj_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, n_ranks = 1, device = 0;
+};
+
+struct rj_state {
+  rj_hyperbolic_module *hm = nullptr;
+  double *U = nullptr;    /* k * ld */
+  double *prec = nullptr; /* n_prec * ld */
+};
+
+/* ------------------------------------------------------------------------ */
+
+struct rj_hyperbolic_module {
+  const rj_offline *od = nullptr;
+  rj_comm *comm = nullptr;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+
+  rj_equation_desc eq{};
+  rj_module_params mp{};
+  InitialValuesDevice iv{};
+
+  double cfl = 0.2; /* hyperbolic_module.template.h:45 */
+  int strategy = RJ_STRATEGY_WARN;
+  uint32_t n_restarts = 0, n_warnings = 0;
+  uint64_t launches = 0;
+
+  int k = 0, n_prec = 0, n_bounds = 0;
+
+  /* scratch, hyperbolic_module.h:319-333 */
+  double *alpha = nullptr, *bounds = nullptr, *r = nullptr;
+  double *dij = nullptr, *lij = nullptr, *lij_next = nullptr, *pij = nullptr;
+  StepScalars *scalars = nullptr;
+  StepScalars *h_scalars = nullptr; /* pinned */
+  double *send_buffer = nullptr;
+  size_t send_buffer_size = 0;
+  double *staging = nullptr; /* n_owned * max(k, n_prec, n_bounds) */
+  uint32_t *csr_to_sliced = nullptr;
+  size_t nnz = 0;
+
+  virtual ~rj_hyperbolic_module();
+  virtual void prepare_state_vector(rj_state &state, double t) = 0;
+  virtual int step(const rj_state &old_state,
+                   int stages,
+                   const rj_state *const *stage_states,
+                   const double *stage_weights,
+                   rj_state &new_state,
+                   double tau,
+                   double tau_max,
+                   double *tau_out) = 0;
+  virtual void interpolate(rj_state &state, double t) = 0;
+
+  StencilView view() const
+  {
+    StencilView v;
+    v.n_owned = od->n_owned;
+    v.ld = od->ld;
+    v.E_owned = od->E_owned;
+    v.slice_offsets = od->slice_offsets;
+    v.row_length = od->row_length;
+    v.cols = od->cols;
+    v.transposed = od->transposed;
+    v.mij = od->mij;
+    v.cij = od->cij;
+    v.mi = od->mi;
+    v.mi_inv = od->mi_inv;
+    v.measure_of_omega_inverse = 1. / od->measure_of_omega;
+    return v;
+  }
+
+  void allocate()
+  {
+    RJ_CUDA(cudaSetDevice(od->device));
+    const size_t ld = od->ld;
+    auto alloc = [&](double *&p, size_t n) {
+      RJ_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double)));
+      RJ_CUDA(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(double), stream));
+    };
+    alloc(alpha, ld);
+    alloc(bounds, size_t(n_bounds) * ld);
+    alloc(r, size_t(k) * ld);
+    alloc(dij, od->E_owned);
+    alloc(lij, od->E_total);
+    alloc(lij_next, od->E_total);
+    alloc(pij, size_t(k) * od->E_owned);
+    RJ_CUDA(cudaMalloc(&scalars, sizeof(StepScalars)));
+    RJ_CUDA(cudaMallocHost(&h_scalars, sizeof(StepScalars)));
+    send_buffer_size =
+        std::max<size_t>(size_t(od->n_send_rows) * std::max(k, std::max(n_prec, n_bounds)),
+                         od->n_mat_send);
+    alloc(send_buffer, send_buffer_size);
+    alloc(staging, size_t(od->n_owned) * std::max(k, std::max(n_prec, n_bounds)));
+    RJ_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  /* -------- launches -------- */
+  template <typename Kernel, typename... Args>
+  void launch(Kernel kernel, size_t n_threads, int block, Args... args)
+  {
+    if (n_threads == 0)
+      return;
+    const unsigned int grid = (unsigned int)((n_threads + block - 1) / block);
+    kernel<<<grid, block, 0, stream>>>(args...);
+    RJ_CUDA(cudaGetLastError());
+    ++launches;
+  }
+
+  /* -------- ghost exchanges (NCCL send/recv groups, cf.
+   * multicomponent_vector / Partitioner::export_to_ghosted_array and
+   * SparseMatrixSIMD::update_ghost_rows, sparse_matrix_simd.h:651-763) -------- */
+  void exchange_vector(double *v, int n_comp)
+  {
+    if (!comm || od->neighbors.empty())
+      return;
+    const size_t ld = od->ld;
+    for (const auto &nb : od->neighbors)
+      launch(k_pack_rows,
+             size_t(nb.send_count) * n_comp,
+             256,
+             nb.send_count,
+             uint32_t(n_comp),
+             uint32_t(ld),
+             od->send_rows + nb.send_offset,
+             v,
+             send_buffer + size_t(nb.send_offset) * n_comp);
+    RJ_NCCL(ncclGroupStart());
+    for (const auto &nb : od->neighbors) {
+      for (int c = 0; c < n_comp; ++c) {
+        if (nb.send_count)
+          RJ_NCCL(ncclSend(send_buffer + size_t(nb.send_offset) * n_comp + size_t(c) * nb.send_count,
+                           nb.send_count,
+                           ncclDouble,
+                           nb.rank,
+                           comm->comm,
+                           stream));
+        if (nb.ghost_count)
+          RJ_NCCL(ncclRecv(v + size_t(c) * ld + nb.ghost_start,
+                           nb.ghost_count,
+                           ncclDouble,
+                           nb.rank,
+                           comm->comm,
+                           stream));
+      }
+    }
+    RJ_NCCL(ncclGroupEnd());
+  }
+
+  void exchange_matrix(double *m)
+  {
+    if (!comm || od->neighbors.empty())
+      return;
+    for (const auto &nb : od->neighbors)
+      launch(k_pack_entries,
+             nb.mat_send_count,
+             256,
+             nb.mat_send_count,
+             od->mat_send_entries + nb.mat_send_offset,
+             m,
+             send_buffer + nb.mat_send_offset);
+    RJ_NCCL(ncclGroupStart());
+    for (const auto &nb : od->neighbors) {
+      if (nb.mat_send_count)
+        RJ_NCCL(ncclSend(send_buffer + nb.mat_send_offset,
+                         nb.mat_send_count,
+                         ncclDouble,
+                         nb.rank,
+                         comm->comm,
+                         stream));
+      if (nb.mat_recv_count)
+        RJ_NCCL(ncclRecv(
+            m + nb.mat_recv_offset, nb.mat_recv_count, ncclDouble, nb.rank, comm->comm, stream));
+    }
+    RJ_NCCL(ncclGroupEnd());
+  }
+
+  void ensure_csr_map()
+  {
+    if (csr_to_sliced)
+      return;
+    std::vector<uint32_t> map;
+    for (uint32_t i = 0; i < od->n_owned; ++i)
+      for (uint32_t c = 0; c < od->h_row_length[i]; ++c)
+        map.push_back(od->entry(i, c));
+    nnz = map.size();
+    RJ_CUDA(cudaMalloc(&csr_to_sliced, std::max<size_t>(nnz, 1) * sizeof(uint32_t)));
+    RJ_CUDA(cudaMemcpy(csr_to_sliced, map.data(), nnz * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+};
+
+rj_hyperbolic_module::~rj_hyperbolic_module()
+{
+  if (od)
+    cudaSetDevice(od->device);
+  auto f = [](void *p) {
+    if (p)
+      cudaFree(p);
+  };
+  f(alpha);
+  f(bounds);
+  f(r);
+  f(dij);
+  f(lij);
+  f(lij_next);
+  f(pij);
+  f(scalars);
+  f(send_buffer);
+  f(staging);
+  f(csr_to_sliced);
+  if (h_scalars)
+    cudaFreeHost(h_scalars);
+  if (owns_stream && stream)
+    cudaStreamDestroy(stream);
+}
+
+namespace rjb
+{
+  template <class Eq>
+  typename Eq::Params make_params(const rj_equation_desc &eq, const rj_module_params &mp);
+
+  template <int dim>
+  EulerParams make_euler_params(const rj_equation_desc &eq, const rj_module_params &mp)
+  {
+    EulerParams p;
+    p.gamma = eq.gamma;
+    p.gamma_inverse = 1. / eq.gamma;
+    p.gamma_plus_one_inverse = 1. / (eq.gamma + 1.);
+    p.gamma_minus_one_inverse = 1. / (eq.gamma - 1.);
+    p.reference_density = eq.reference_density;
+    p.vacuum_relaxation_small = eq.vacuum_state_relaxation_small;
+    p.vacuum_relaxation_large = eq.vacuum_state_relaxation_large;
+    p.evc_factor = mp.indicator_evc_factor;
+    p.limiter_newton_tolerance = mp.limiter_newton_tolerance;
+    p.limiter_relaxation_factor = mp.limiter_relaxation_factor;
+    p.limiter_newton_max_iterations = mp.limiter_newton_max_iterations;
+    p.riemann_newton_tolerance = mp.riemann_newton_tolerance;
+    p.riemann_newton_max_iterations = mp.riemann_newton_max_iterations;
+    return p;
+  }
+
+  template <>
+  EulerParams make_params<Euler<1>>(const rj_equation_desc &eq, const rj_module_params &mp)
+  {
+    return make_euler_params<1>(eq, mp);
+  }
+  template <>
+  EulerParams make_params<Euler<2>>(const rj_equation_desc &eq, const rj_module_params &mp)
+  {
+    return make_euler_params<2>(eq, mp);
+  }
+  template <>
+  EulerParams make_params<Euler<3>>(const rj_equation_desc &eq, const rj_module_params &mp)
+  {
+    return make_euler_params<3>(eq, mp);
+  }
+
+
+  template <class Eq>
+  struct ModuleImpl : rj_hyperbolic_module {
+    typename Eq::Params prm;
+    static constexpr int block = 128;
+
+    ModuleImpl()
+    {
+      k = Eq::k;
+      n_prec = Eq::n_prec;
+      n_bounds = Eq::n_bounds;
+    }
+
+    /* rows [begin, end), begin multiple of 32 */
+    template <typename Kernel, typename... Args>
+    void launch_rows(Kernel kernel, uint32_t begin, uint32_t end, Args... args)
+    {
+      if (end > begin)
+        launch(kernel, end - begin, block, args...);
+    }
+
+    void interpolate(rj_state &state, double t) override
+    {
+      if (!od->positions)
+        throw InvalidArgument("rj_state_interpolate: offline data has no positions");
+      launch(k_interpolate<Eq, InitialValuesDevice>,
+             od->n_owned,
+             256,
+             od->n_owned,
+             od->ld,
+             od->positions,
+             prm,
+             iv,
+             t,
+             state.U);
+    }
+
+    /* hyperbolic_module.template.h:97-193 */
+    void prepare_state_vector(rj_state &state, double t) override
+    {
+      RJ_CUDA(cudaSetDevice(od->device));
+      const StencilView v = view();
+      launch(k_apply_boundary_conditions<Eq, InitialValuesDevice>,
+             od->n_bgroups,
+             128,
+             od->n_bgroups,
+             od->bgroup_dof,
+             od->bgroup_start,
+             od->bnormal,
+             od->bposition,
+             od->bid,
+             od->ld,
+             prm,
+             iv,
+             t,
+             state.U);
+      exchange_vector(state.U, Eq::k); /* C1 */
+      launch_rows(k_precompute<Eq>, 0, od->n_owned, v, prm, 0u, od->n_owned, state.U, state.prec);
+      exchange_vector(state.prec, Eq::n_prec); /* C2 */
+    }
+
+    template <int stages>
+    void low_order(const rj_state &old_state,
+                   const rj_state *const *stage_states,
+                   const double *stage_weights,
+                   rj_state &new_state)
+    {
+      StagePointers<stages> st{};
+      for (int s = 0; s < stages; ++s) {
+        st.U[s] = stage_states[s]->U;
+        st.prec[s] = stage_states[s]->prec;
+        st.weight[s] = stage_weights[s];
+      }
+      launch_rows(k_low_order<Eq, stages>,
+                  0,
+                  od->n_owned,
+                  view(),
+                  prm,
+                  0u,
+                  od->n_owned,
+                  old_state.U,
+                  old_state.prec,
+                  st,
+                  alpha,
+                  dij,
+                  scalars,
+                  new_state.U,
+                  r,
+                  bounds,
+                  pij);
+    }
+
+    /* hyperbolic_module.template.h:236-1211 */
+    int step(const rj_state &old_state,
+             int stages,
+             const rj_state *const *stage_states,
+             const double *stage_weights,
+             rj_state &new_state,
+             double tau,
+             double tau_max_in,
+             double *tau_out) override
+    {
+      RJ_CUDA(cudaSetDevice(od->device));
+      if (stages < 0 || stages > 4)
+        throw InvalidArgument("rj_hyperbolic_module_step: stages must be in [0, 4]");
+      if (old_state.U == new_state.U)
+        throw InvalidArgument("rj_hyperbolic_module_step: old and new state must differ");
+      const StencilView v = view();
+      const uint32_t n_owned = od->n_owned;
+
+      launch(k_reset_scalars, 1, 1, scalars);
+
+      /* Step 2: d_ij (j > i), alpha_i; then C3 */
+      launch_rows(k_dij_alpha<Eq>, 0, n_owned, v, prm, 0u, n_owned, old_state.U, old_state.prec, dij, alpha);
+      exchange_vector(alpha, 1);
+
+      /* Step 3: boundary d_ij, d_ii, tau_max; C4 */
+      launch(k_boundary_dij<Eq>,
+             od->n_pairs,
+             128,
+             od->n_pairs,
+             od->pair_i,
+             od->pair_j,
+             od->pair_e,
+             od->pair_eT,
+             od->pair_cji,
+             od->ld,
+             od->E_owned,
+             prm,
+             old_state.U,
+             old_state.prec,
+             dij);
+      launch_rows(k_dii_tau, 0, n_owned, v, 0u, n_owned, cfl, dij, scalars);
+      launch(k_tau_local, 1, 1, scalars, tau_max_in);
+      if (comm && comm->n_ranks > 1)
+        RJ_NCCL(ncclAllReduce(
+            &scalars->tau_max, &scalars->tau_max, 1, ncclDouble, ncclMin, comm->comm, stream));
+      launch(k_tau_finalize, 1, 1, scalars, tau);
+
+      /* Step 4: low-order update, bounds, r_i, P_ij; C6 */
+      switch (stages) {
+      case 0: low_order<0>(old_state, stage_states, stage_weights, new_state); break;
+      case 1: low_order<1>(old_state, stage_states, stage_weights, new_state); break;
+      case 2: low_order<2>(old_state, stage_states, stage_weights, new_state); break;
+      case 3: low_order<3>(old_state, stage_states, stage_weights, new_state); break;
+      case 4: low_order<4>(old_state, stage_states, stage_weights, new_state); break;
+      }
+      exchange_vector(r, Eq::k);
+
+      /* Step 5: P_ij correction and first l_ij; C7 */
+      const unsigned int n_iterations = mp.limiter_iterations;
+      if (n_iterations != 0) {
+        launch_rows(k_pij_lij<Eq>, 0, n_owned, v, prm, 0u, n_owned, new_state.U, r, bounds, scalars, pij, lij);
+        exchange_matrix(lij);
+      }
+
+      /* Steps 6, 7; C8 */
+      for (unsigned int pass = 0; pass < n_iterations; ++pass) {
+        const bool last_round = (pass + 1 == n_iterations);
+        if ((n_iterations == 2) && last_round)
+          std::swap(lij, lij_next);
+        if (last_round)
+          launch_rows(k_high_order<Eq, true>, 0, n_owned, v, prm, 0u, n_owned, bounds, pij, lij, lij_next, new_state.U);
+        else {
+          launch_rows(k_high_order<Eq, false>, 0, n_owned, v, prm, 0u, n_owned, bounds, pij, lij, lij_next, new_state.U);
+          exchange_matrix(lij_next);
+        }
+      }
+
+      /* C9 and the host side of :571-578,1190-1210 */
+      if (comm && comm->n_ranks > 1)
+        RJ_NCCL(ncclAllReduce(&scalars->restart_needed,
+                              &scalars->restart_needed,
+                              1,
+                              ncclInt,
+                              ncclMax,
+                              comm->comm,
+                              stream));
+      RJ_CUDA(cudaMemcpyAsync(h_scalars, scalars, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
+      RJ_CUDA(cudaStreamSynchronize(stream));
+
+      if (h_scalars->numeric_error)
+        throw NumericError("I'm sorry, Dave. I'm afraid I can't do that.\nWe crashed. "
+                           "(tau_max is nan, inf or not positive)");
+      *tau_out = h_scalars->tau;
+
+      if (h_scalars->restart_needed) {
+        if (strategy == RJ_STRATEGY_WARN)
+          n_warnings++;
+        else {
+          n_restarts++;
+          return RJ_RESTART;
+        }
+      }
+      return RJ_OK;
+    }
+  };
+
+
+  /* TimeIntegrator, source/time_integrator.template.h:207-443 */
+  struct TimeIntegrator {
+    rj_hyperbolic_module *hm;
+    int scheme;
+    double cfl_min, cfl_max;
+    int recovery;
+    double efficiency = 1.;
+    std::vector<rj_state *> temp;
+
+    double t = 0.;
+
+    int hstep(const rj_state &old_state,
+              std::vector<const rj_state *> st,
+              std::vector<double> w,
+              rj_state &new_state,
+              double tau,
+              double tau_max,
+              double &tau_out)
+    {
+      return hm->step(old_state, int(st.size()), st.data(), w.data(), new_state, tau, tau_max, &tau_out);
+    }
+  };
+} // namespace rjb
+
+struct rj_time_integrator : rjb::TimeIntegrator {
+};
+
+namespace rjb
+{
+  constexpr double no_tau_max = DBL_MAX;
+
+  /* Each scheme returns RJ_OK / RJ_RESTART and the total step in tau_out. */
+  int single_step(rj_time_integrator &ti, rj_state &sv, double t, double tau_max, double &tau_out)
+  {
+    auto &hm = *ti.hm;
+    auto &T = ti.temp;
+    double tau = 0., dummy = 0.;
+    int rc;
+#define RJ_TRY(expr)                                                                               \
+  do {                                                                                             \
+    rc = (expr);                                                                                   \
+    if (rc != RJ_OK)                                                                               \
+      return rc;                                                                                   \
+  } while (0)
+
+    switch (ti.scheme) {
+    case RJ_SSPRK_22:
+      hm.prepare_state_vector(sv, t);
+      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max, tau));
+      hm.prepare_state_vector(*T[0], t + 1.0 * tau);
+      RJ_TRY(ti.hstep(*T[0], {}, {}, *T[1], tau, no_tau_max, dummy));
+      rj_state_sadd(T[1], 1.0 / 2.0, 1.0 / 2.0, &sv);
+      rj_state_swap(&sv, T[1]);
+      tau_out = tau;
+      return RJ_OK;
+    case RJ_SSPRK_33:
+      hm.prepare_state_vector(sv, t);
+      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max, tau));
+      hm.prepare_state_vector(*T[0], t + 1.0 * tau);
+      RJ_TRY(ti.hstep(*T[0], {}, {}, *T[1], tau, no_tau_max, dummy));
+      rj_state_sadd(T[1], 1.0 / 4.0, 3.0 / 4.0, &sv);
+      hm.prepare_state_vector(*T[1], t + 0.5 * tau);
+      RJ_TRY(ti.hstep(*T[1], {}, {}, *T[0], tau, no_tau_max, dummy));
+      rj_state_sadd(T[0], 2.0 / 3.0, 1.0 / 3.0, &sv);
+      rj_state_swap(&sv, T[0]);
+      tau_out = tau;
+      return RJ_OK;
+    case RJ_ERK_11:
+      hm.prepare_state_vector(sv, t);
+      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max, tau));
+      rj_state_swap(&sv, T[0]);
+      tau_out = tau;
+      return RJ_OK;
+    case RJ_ERK_22:
+      hm.prepare_state_vector(sv, t);
+      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max / 2., tau));
+      hm.prepare_state_vector(*T[0], t + 1.0 * tau);
+      RJ_TRY(ti.hstep(*T[0], {&sv}, {-1.}, *T[1], tau, no_tau_max, dummy));
+      rj_state_swap(&sv, T[1]);
+      tau_out = 2. * tau;
+      return RJ_OK;
+    case RJ_ERK_33:
+      hm.prepare_state_vector(sv, t);
+      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max / 3., tau));
+      hm.prepare_state_vector(*T[0], t + 1.0 * tau);
+      RJ_TRY(ti.hstep(*T[0], {&sv}, {-1.}, *T[1], tau, no_tau_max, dummy));
+      hm.prepare_state_vector(*T[1], t + 2.0 * tau);
+      RJ_TRY(ti.hstep(*T[1], {&sv, T[0]}, {0.75, -2.}, *T[2], tau, no_tau_max, dummy));
+      rj_state_swap(&sv, T[2]);
+      tau_out = 3. * tau;
+      return RJ_OK;
+    case RJ_ERK_43:
+      hm.prepare_state_vector(sv, t);
+      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max / 4., tau));
+      hm.prepare_state_vector(*T[0], t + 1.0 * tau);
+      RJ_TRY(ti.hstep(*T[0], {&sv}, {-1.}, *T[1], tau, no_tau_max, dummy));
+      hm.prepare_state_vector(*T[1], t + 2.0 * tau);
+      RJ_TRY(ti.hstep(*T[1], {T[0]}, {-1.}, *T[2], tau, no_tau_max, dummy));
+      hm.prepare_state_vector(*T[2], t + 3.0 * tau);
+      RJ_TRY(ti.hstep(*T[2], {T[0], T[1]}, {5. / 3., -10. / 3.}, *T[3], tau, no_tau_max, dummy));
+      rj_state_swap(&sv, T[3]);
+      tau_out = 4. * tau;
+      return RJ_OK;
+    }
+#undef RJ_TRY
+    throw InvalidArgument("rj_time_integrator_step: unknown time stepping scheme");
+  }
+} // namespace rjb
+
+
+/* ======================================================================== *
+ *                              extern "C"
+ * ======================================================================== */
+
+extern "C" {
+
+const char *rj_last_error(void) { return g_last_error.c_str(); }
+
+int rj_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char *rj_version(void) { return "ryujin_b200 0.1 (sm_100a)"; }
+
+int rj_offline_create(rj_offline **out, const rj_offline_desc *desc, int device)
+{
+  return guarded([&] {
+    if (!out || !desc)
+      throw InvalidArgument("rj_offline_create: null argument");
+    *out = build_device_offline(*desc, device);
+    return RJ_OK;
+  });
+}
+
+void rj_offline_destroy(rj_offline *od) { delete od; }
+
+int rj_offline_layout_sizes(const rj_offline *od, uint64_t sizes[4])
+{
+  return guarded([&] {
+    if (!od)
+      throw InvalidArgument("null offline data");
+    sizes[0] = od->n_slices;
+    sizes[1] = od->E_owned;
+    sizes[2] = od->E_total;
+    sizes[3] = od->ld;
+    return RJ_OK;
+  });
+}
+
+int rj_offline_layout_get(const rj_offline *od,
+                          uint64_t *slice_offsets,
+                          uint32_t *row_length,
+                          uint32_t *cols,
+                          uint32_t *transposed)
+{
+  return guarded([&] {
+    if (!od)
+      throw InvalidArgument("null offline data");
+    RJ_CUDA(cudaSetDevice(od->device));
+    if (slice_offsets)
+      for (uint32_t g = 0; g <= od->n_slices; ++g)
+        slice_offsets[g] = od->h_slice_offsets[g];
+    if (row_length)
+      for (uint32_t i = 0; i < od->n_owned; ++i)
+        row_length[i] = od->h_row_length[i];
+    if (cols)
+      RJ_CUDA(cudaMemcpy(cols, od->cols, size_t(od->E_owned) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (transposed)
+      RJ_CUDA(cudaMemcpy(
+          transposed, od->transposed, size_t(od->E_owned) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return RJ_OK;
+  });
+}
+
+/* ---- communicator ---- */
+
+int rj_comm_unique_id(uint8_t id[RJ_UNIQUE_ID_BYTES])
+{
+  return guarded([&] {
+    static_assert(sizeof(ncclUniqueId) <= RJ_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId uid;
+    RJ_NCCL(ncclGetUniqueId(&uid));
+    std::memset(id, 0, RJ_UNIQUE_ID_BYTES);
+    std::memcpy(id, &uid, sizeof(uid));
+    return RJ_OK;
+  });
+}
+
+int rj_comm_create(rj_comm **out, const uint8_t id[RJ_UNIQUE_ID_BYTES], int rank, int n_ranks, int device)
+{
+  return guarded([&] {
+    if (!out || !id)
+      throw InvalidArgument("rj_comm_create: null argument");
+    if (rj_device_count() == 0)
+      throw NoDevice("rj_comm_create: no CUDA device");
+    RJ_CUDA(cudaSetDevice(device));
+    auto c = std::unique_ptr<rj_comm>(new rj_comm());
+    c->rank = rank;
+    c->n_ranks = n_ranks;
+    c->device = device;
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    RJ_NCCL(ncclCommInitRank(&c->comm, n_ranks, uid, rank));
+    *out = c.release();
+    return RJ_OK;
+  });
+}
+
+void rj_comm_destroy(rj_comm *c)
+{
+  if (!c)
+    return;
+  if (c->comm)
+    ncclCommDestroy(c->comm);
+  delete c;
+}
+
+/* ---- parameter defaults ---- */
+
+void rj_equation_desc_default(rj_equation_desc *eq, int equation)
+{
+  std::memset(eq, 0, sizeof(*eq));
+  eq->equation = equation;
+  eq->gamma = 7. / 5.;
+  eq->reference_density = 1.;
+  eq->vacuum_state_relaxation_small = 1.e2;
+  eq->vacuum_state_relaxation_large = 1.e4;
+  eq->gravity = 9.81;
+  eq->manning_friction_coefficient = 0.;
+  eq->reference_water_depth = 1.;
+  eq->dry_state_relaxation_small = 1.e2;
+  eq->dry_state_relaxation_large = 1.e4;
+}
+
+void rj_module_params_default(rj_module_params *mp)
+{
+  mp->indicator_evc_factor = 1.;
+  mp->limiter_iterations = 2;
+  mp->limiter_newton_tolerance = 1.e-10;
+  mp->limiter_newton_max_iterations = 2;
+  mp->limiter_relaxation_factor = 1.;
+  mp->riemann_newton_tolerance = 1.e-10;
+  mp->riemann_newton_max_iterations = 0;
+}
+
+void rj_initial_values_desc_default(rj_initial_values_desc *iv, int kind)
+{
+  std::memset(iv, 0, sizeof(*iv));
+  iv->kind = kind;
+  iv->direction[0] = 1.;
+  iv->position[0] = 1.;
+  iv->primitive[0] = 1.4;
+  iv->primitive[1] = kind == RJ_INITIAL_UNIFORM ? 3. : 0.;
+  iv->primitive[2] = 1.;
+  iv->primitive_right[0] = 1.4;
+  iv->primitive_right[1] = 0.;
+  iv->primitive_right[2] = 1.;
+  iv->mach_number = 2.;
+  iv->beta = 5.;
+}
+
+/* ---- module ---- */
+
+int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
+                                const rj_offline *od,
+                                const rj_equation_desc *eq,
+                                const rj_module_params *mp,
+                                const rj_initial_values_desc *iv,
+                                rj_comm *comm,
+                                void *stream)
+{
+  return guarded([&] {
+    if (!out || !od || !eq || !mp || !iv)
+      throw InvalidArgument("rj_hyperbolic_module_create: null argument");
+    if (mp->limiter_iterations > 2)
+      throw InvalidArgument("The number of limiter iterations must be between [0,2]");
+    if (!od->neighbors.empty() && !comm)
+      throw InvalidArgument("rj_hyperbolic_module_create: offline data has ghost rows but comm is NULL");
+    RJ_CUDA(cudaSetDevice(od->device));
+
+    std::unique_ptr<rj_hyperbolic_module> hm;
+    auto make = [&](auto tag) {
+      using Eq = decltype(tag);
+      auto *m = new ModuleImpl<Eq>();
+      m->prm = make_params<Eq>(*eq, *mp);
+      hm.reset(m);
+    };
+    if (eq->equation == RJ_EQUATION_EULER) {
+      if (od->dim == 1)
+        make(Euler<1>());
+      else if (od->dim == 2)
+        make(Euler<2>());
+      else
+        make(Euler<3>());
+    } else
+      throw InvalidArgument("rj_hyperbolic_module_create: equation module not available");
+
+    hm->od = od;
+    hm->comm = comm;
+    hm->eq = *eq;
+    hm->mp = *mp;
+    if (stream)
+      hm->stream = static_cast<cudaStream_t>(stream);
+    else {
+      RJ_CUDA(cudaStreamCreateWithFlags(&hm->stream, cudaStreamNonBlocking));
+      hm->owns_stream = true;
+    }
+
+    /* InitialValues::parse_parameters_callback: normalize direction */
+    InitialValuesDevice &d = hm->iv;
+    d.kind = iv->kind;
+    double nrm = 0.;
+    for (int q = 0; q < od->dim; ++q)
+      nrm += iv->direction[q] * iv->direction[q];
+    nrm = std::sqrt(nrm);
+    if (nrm == 0.)
+      throw InvalidArgument("Initial direction is set to the zero vector.");
+    for (int q = 0; q < 3; ++q) {
+      d.direction[q] = q < od->dim ? iv->direction[q] / nrm : 0.;
+      d.position[q] = q < od->dim ? iv->position[q] : 0.;
+      d.primitive[q] = iv->primitive[q];
+      d.primitive_right[q] = iv->primitive_right[q];
+    }
+    d.mach_number = iv->mach_number;
+    d.beta = iv->beta;
+    for (int q = 0; q < 4; ++q)
+      d.sw[q] = iv->sw_params[q];
+
+    hm->allocate();
+    *out = hm.release();
+    return RJ_OK;
+  });
+}
+
+void rj_hyperbolic_module_destroy(rj_hyperbolic_module *hm) { delete hm; }
+
+int rj_hyperbolic_module_prepare_state_vector(rj_hyperbolic_module *hm, rj_state *state, double t)
+{
+  return guarded([&] {
+    if (!hm || !state)
+      throw InvalidArgument("null argument");
+    hm->prepare_state_vector(*state, t);
+    return RJ_OK;
+  });
+}
+
+int rj_hyperbolic_module_step(rj_hyperbolic_module *hm,
+                              const rj_state *old_state,
+                              int stages,
+                              const rj_state *const *stage_states,
+                              const double *stage_weights,
+                              rj_state *new_state,
+                              double tau,
+                              double tau_max,
+                              double *tau_out)
+{
+  return guarded([&] {
+    if (!hm || !old_state || !new_state || !tau_out)
+      throw InvalidArgument("null argument");
+    return hm->step(*old_state, stages, stage_states, stage_weights, *new_state, tau, tau_max, tau_out);
+  });
+}
+
+int rj_hyperbolic_module_set_cfl(rj_hyperbolic_module *hm, double cfl)
+{
+  return guarded([&] {
+    if (!hm || !(cfl > 0.))
+      throw InvalidArgument("rj_hyperbolic_module_set_cfl: invalid argument");
+    hm->cfl = cfl;
+    return RJ_OK;
+  });
+}
+
+double rj_hyperbolic_module_cfl(const rj_hyperbolic_module *hm) { return hm->cfl; }
+
+int rj_hyperbolic_module_set_id_violation_strategy(rj_hyperbolic_module *hm, int strategy)
+{
+  return guarded([&] {
+    if (!hm || (strategy != RJ_STRATEGY_WARN && strategy != RJ_STRATEGY_RAISE_EXCEPTION))
+      throw InvalidArgument("invalid id violation strategy");
+    hm->strategy = strategy;
+    return RJ_OK;
+  });
+}
+
+int rj_hyperbolic_module_counters(const rj_hyperbolic_module *hm, uint32_t *n_restarts, uint32_t *n_warnings)
+{
+  return guarded([&] {
+    if (!hm)
+      throw InvalidArgument("null argument");
+    if (n_restarts)
+      *n_restarts = hm->n_restarts;
+    if (n_warnings)
+      *n_warnings = hm->n_warnings;
+    return RJ_OK;
+  });
+}
+
+const double *rj_hyperbolic_module_device_alpha(const rj_hyperbolic_module *hm) { return hm->alpha; }
+
+int rj_hyperbolic_module_synchronize(rj_hyperbolic_module *hm)
+{
+  return guarded([&] {
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    RJ_CUDA(cudaStreamSynchronize(hm->stream));
+    return RJ_OK;
+  });
+}
+
+void *rj_hyperbolic_module_stream(rj_hyperbolic_module *hm) { return hm->stream; }
+
+int rj_hyperbolic_module_sizes(const rj_hyperbolic_module *hm, uint64_t out[6])
+{
+  return guarded([&] {
+    if (!hm)
+      throw InvalidArgument("null argument");
+    out[0] = hm->k;
+    out[1] = hm->n_prec;
+    out[2] = hm->n_bounds;
+    out[3] = hm->od->n_owned;
+    out[4] = hm->od->ld;
+    out[5] = hm->od->E_owned;
+    return RJ_OK;
+  });
+}
+
+uint64_t rj_hyperbolic_module_kernel_launches(const rj_hyperbolic_module *hm) { return hm->launches; }
+
+int rj_hyperbolic_module_get_scratch(rj_hyperbolic_module *hm, int what, double *host_out)
+{
+  return guarded([&] {
+    if (!hm || !host_out)
+      throw InvalidArgument("null argument");
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    const auto *od = hm->od;
+    const uint32_t n = od->n_owned, ld = od->ld;
+    auto vector_out = [&](const double *v, int n_comp) {
+      hm->launch(k_soa_to_aos, size_t(n) * n_comp, 256, n, uint32_t(n_comp), ld, v, hm->staging);
+      RJ_CUDA(cudaMemcpyAsync(
+          host_out, hm->staging, size_t(n) * n_comp * sizeof(double), cudaMemcpyDeviceToHost, hm->stream));
+      RJ_CUDA(cudaStreamSynchronize(hm->stream));
+    };
+    auto matrix_out = [&](const double *m, int n_comp) {
+      hm->ensure_csr_map();
+      double *tmp = nullptr;
+      RJ_CUDA(cudaMalloc(&tmp, std::max<size_t>(hm->nnz, 1) * sizeof(double)));
+      std::vector<double> h(hm->nnz);
+      for (int c = 0; c < n_comp; ++c) {
+        hm->launch(k_gather_entries, hm->nnz, 256, hm->nnz, hm->csr_to_sliced, m + size_t(c) * od->E_owned, tmp);
+        RJ_CUDA(cudaMemcpyAsync(h.data(), tmp, hm->nnz * sizeof(double), cudaMemcpyDeviceToHost, hm->stream));
+        RJ_CUDA(cudaStreamSynchronize(hm->stream));
+        for (size_t e = 0; e < hm->nnz; ++e)
+          host_out[e * n_comp + c] = h[e];
+      }
+      cudaFree(tmp);
+    };
+    switch (what) {
+    case 0: vector_out(hm->alpha, 1); break;
+    case 1: matrix_out(hm->dij, 1); break;
+    case 2: matrix_out(hm->lij, 1); break;
+    case 3: matrix_out(hm->lij_next, 1); break;
+    case 4: matrix_out(hm->pij, hm->k); break;
+    case 5: vector_out(hm->r, hm->k); break;
+    case 6: vector_out(hm->bounds, hm->n_bounds); break;
+    default: throw InvalidArgument("rj_hyperbolic_module_get_scratch: unknown id");
+    }
+    return RJ_OK;
+  });
+}
+
+/* ---- state vectors ---- */
+
+int rj_state_create(rj_state **out, rj_hyperbolic_module *hm)
+{
+  return guarded([&] {
+    if (!out || !hm)
+      throw InvalidArgument("null argument");
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    auto s = std::unique_ptr<rj_state>(new rj_state());
+    s->hm = hm;
+    const size_t ld = hm->od->ld;
+    RJ_CUDA(cudaMalloc(&s->U, size_t(hm->k) * ld * sizeof(double)));
+    RJ_CUDA(cudaMalloc(&s->prec, size_t(hm->n_prec) * ld * sizeof(double)));
+    RJ_CUDA(cudaMemsetAsync(s->U, 0, size_t(hm->k) * ld * sizeof(double), hm->stream));
+    RJ_CUDA(cudaMemsetAsync(s->prec, 0, size_t(hm->n_prec) * ld * sizeof(double), hm->stream));
+    RJ_CUDA(cudaStreamSynchronize(hm->stream));
+    *out = s.release();
+    return RJ_OK;
+  });
+}
+
+void rj_state_destroy(rj_state *s)
+{
+  if (!s)
+    return;
+  cudaSetDevice(s->hm->od->device);
+  cudaFree(s->U);
+  cudaFree(s->prec);
+  delete s;
+}
+
+int rj_state_upload(rj_state *s, const double *host_U)
+{
+  return guarded([&] {
+    if (!s || !host_U)
+      throw InvalidArgument("null argument");
+    auto *hm = s->hm;
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    const uint32_t n = hm->od->n_owned, k = hm->k;
+    RJ_CUDA(cudaMemcpyAsync(
+        hm->staging, host_U, size_t(n) * k * sizeof(double), cudaMemcpyHostToDevice, hm->stream));
+    hm->launch(k_aos_to_soa, size_t(n) * k, 256, n, k, hm->od->ld, hm->staging, s->U);
+    RJ_CUDA(cudaStreamSynchronize(hm->stream));
+    return RJ_OK;
+  });
+}
+
+int rj_state_download(const rj_state *s, double *host_U)
+{
+  return guarded([&] {
+    if (!s || !host_U)
+      throw InvalidArgument("null argument");
+    auto *hm = s->hm;
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    const uint32_t n = hm->od->n_owned, k = hm->k;
+    hm->launch(k_soa_to_aos, size_t(n) * k, 256, n, k, hm->od->ld, s->U, hm->staging);
+    RJ_CUDA(cudaMemcpyAsync(
+        host_U, hm->staging, size_t(n) * k * sizeof(double), cudaMemcpyDeviceToHost, hm->stream));
+    RJ_CUDA(cudaStreamSynchronize(hm->stream));
+    return RJ_OK;
+  });
+}
+
+int rj_state_download_precomputed(const rj_state *s, double *host_prec)
+{
+  return guarded([&] {
+    if (!s || !host_prec)
+      throw InvalidArgument("null argument");
+    auto *hm = s->hm;
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    const uint32_t n = hm->od->n_owned, k = hm->n_prec;
+    hm->launch(k_soa_to_aos, size_t(n) * k, 256, n, k, hm->od->ld, s->prec, hm->staging);
+    RJ_CUDA(cudaMemcpyAsync(
+        host_prec, hm->staging, size_t(n) * k * sizeof(double), cudaMemcpyDeviceToHost, hm->stream));
+    RJ_CUDA(cudaStreamSynchronize(hm->stream));
+    return RJ_OK;
+  });
+}
+
+int rj_state_interpolate(rj_state *s, double t)
+{
+  return guarded([&] {
+    if (!s)
+      throw InvalidArgument("null argument");
+    RJ_CUDA(cudaSetDevice(s->hm->od->device));
+    s->hm->interpolate(*s, t);
+    return RJ_OK;
+  });
+}
+
+double *rj_state_device_U(rj_state *s) { return s->U; }
+double *rj_state_device_precomputed(rj_state *s) { return s->prec; }
+
+int rj_state_sadd(rj_state *dst, double s, double b, const rj_state *src)
+{
+  return guarded([&] {
+    if (!dst || !src || dst->hm != src->hm)
+      throw InvalidArgument("rj_state_sadd: states of different modules");
+    auto *hm = dst->hm;
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    const size_t n = size_t(hm->k) * hm->od->ld;
+    hm->launch(k_sadd, n, 256, n, s, b, dst->U, src->U);
+    return RJ_OK;
+  });
+}
+
+int rj_state_swap(rj_state *a, rj_state *b)
+{
+  return guarded([&] {
+    if (!a || !b || a->hm != b->hm)
+      throw InvalidArgument("rj_state_swap: states of different modules");
+    std::swap(a->U, b->U);
+    std::swap(a->prec, b->prec);
+    return RJ_OK;
+  });
+}
+
+/* ---- time integrator ---- */
+
+int rj_time_integrator_create(rj_time_integrator **out,
+                              rj_hyperbolic_module *hm,
+                              int scheme,
+                              double cfl_min,
+                              double cfl_max,
+                              int cfl_recovery_strategy)
+{
+  return guarded([&] {
+    if (!out || !hm)
+      throw InvalidArgument("null argument");
+    if (!(cfl_min > 0.))
+      throw InvalidArgument("cfl min must be a positive value");
+    if (!(cfl_max >= cfl_min))
+      throw InvalidArgument("cfl max must be greater than or equal to cfl min");
+    auto ti = std::unique_ptr<rj_time_integrator>(new rj_time_integrator());
+    ti->hm = hm;
+    ti->scheme = scheme;
+    ti->cfl_min = cfl_min;
+    ti->cfl_max = cfl_max;
+    ti->recovery = cfl_recovery_strategy;
+    int n_temp = 0;
+    switch (scheme) { /* time_integrator.template.h:87-137 */
+    case RJ_SSPRK_22: n_temp = 2; ti->efficiency = 1.; break;
+    case RJ_SSPRK_33: n_temp = 2; ti->efficiency = 1.; break;
+    case RJ_ERK_11: n_temp = 1; ti->efficiency = 1.; break;
+    case RJ_ERK_22: n_temp = 2; ti->efficiency = 2.; break;
+    case RJ_ERK_33: n_temp = 3; ti->efficiency = 3.; break;
+    case RJ_ERK_43: n_temp = 4; ti->efficiency = 4.; break;
+    default: throw InvalidArgument("unknown time stepping scheme");
+    }
+    for (int i = 0; i < n_temp; ++i) {
+      rj_state *s = nullptr;
+      const int rc = rj_state_create(&s, hm);
+      if (rc != RJ_OK)
+        throw CudaError(g_last_error);
+      ti->temp.push_back(s);
+    }
+    hm->cfl = cfl_max;
+    *out = ti.release();
+    return RJ_OK;
+  });
+}
+
+void rj_time_integrator_destroy(rj_time_integrator *ti)
+{
+  if (!ti)
+    return;
+  for (auto *s : ti->temp)
+    rj_state_destroy(s);
+  delete ti;
+}
+
+/* time_integrator.template.h:207-275 */
+int rj_time_integrator_step(rj_time_integrator *ti, rj_state *state, double t, double t_final, double *tau_out)
+{
+  return guarded([&] {
+    if (!ti || !state || !tau_out)
+      throw InvalidArgument("null argument");
+    auto &hm = *ti->hm;
+    const double tau_max = t_final < 0. ? DBL_MAX : t_final - t;
+
+    if (ti->recovery == RJ_CFL_RECOVERY_BANG_BANG) {
+      hm.strategy = RJ_STRATEGY_RAISE_EXCEPTION;
+      hm.cfl = ti->cfl_max;
+    }
+    double tau = 0.;
+    int rc = single_step(*ti, *state, t, tau_max, tau);
+    if (rc == RJ_RESTART) {
+      if (ti->recovery == RJ_CFL_RECOVERY_NONE)
+        throw InvalidArgument("Restart raised with cfl recovery strategy none");
+      hm.strategy = RJ_STRATEGY_WARN;
+      hm.cfl = ti->cfl_min;
+      rc = single_step(*ti, *state, t, tau_max, tau);
+    }
+    *tau_out = tau;
+    return rc;
+  });
+}
+
+double rj_time_integrator_efficiency(const rj_time_integrator *ti) { return ti->efficiency; }
+
+/* ---- host-only entry points: mesh generator, layout decoding ---- */
+
+struct rj_host_offline {
+  rjb::HostOffline data;
+};
+
+int rj_mesh_generate(rj_host_offline **out, const rj_mesh_desc *mesh, int rank, int n_ranks)
+{
+  return guarded([&] {
+    if (!out || !mesh)
+      throw InvalidArgument("rj_mesh_generate: null argument");
+    auto h = std::unique_ptr<rj_host_offline>(new rj_host_offline());
+    generate_cartesian_q1(h->data, *mesh, rank, n_ranks);
+    *out = h.release();
+    return RJ_OK;
+  });
+}
+
+void rj_host_offline_destroy(rj_host_offline *h) { delete h; }
+
+int rj_host_offline_desc(const rj_host_offline *h, rj_offline_desc *desc)
+{
+  return guarded([&] {
+    if (!h || !desc)
+      throw InvalidArgument("null argument");
+    h->data.fill_desc(*desc);
+    return RJ_OK;
+  });
+}
+
+int rj_host_offline_global_indices(const rj_host_offline *h, uint64_t *global)
+{
+  return guarded([&] {
+    if (!h || !global)
+      throw InvalidArgument("null argument");
+    std::memcpy(global, h->data.global_index.data(), h->data.global_index.size() * sizeof(uint64_t));
+    return RJ_OK;
+  });
+}
+
+uint64_t rj_host_offline_n_global_dofs(const rj_host_offline *h) { return h->data.n_global_dofs; }
+
+int rj_decode_simd_pattern(uint32_t n_rows,
+                           uint32_t n_internal,
+                           uint32_t simd_length,
+                           const uint64_t *row_starts,
+                           const uint32_t *column_indices,
+                           uint64_t *csr_row_ptr,
+                           uint32_t *csr_cols)
+{
+  return guarded([&] {
+    std::vector<uint64_t> rp;
+    std::vector<uint32_t> cl;
+    decode_simd_pattern(n_rows, n_internal, simd_length, row_starts, column_indices, rp, cl);
+    std::memcpy(csr_row_ptr, rp.data(), rp.size() * sizeof(uint64_t));
+    std::memcpy(csr_cols, cl.data(), cl.size() * sizeof(uint32_t));
+    return RJ_OK;
+  });
+}
+
+} /* extern "C" */

@@ -1,0 +1,346 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and against the
+reference's own golden outputs.  All tests here need a B200: run with `-m gpu`.
+
+Tolerances (north_star): state within 1e-12 relative L-infinity of the reference path
+after 100 steps; tau sequence within 1e-13; stencil indices bit-exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from helpers import CASES, initial_state_host, make_mesh, make_oracle, make_product, rel_linf, rel_linf_per_component
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_and_oracle(oracle, case, n_cells, **prm):
+    od, module = make_product(case, n_cells, **{k: v for k, v in prm.items() if k in ("gamma",)})
+    off, sim = make_oracle(oracle, case, od.host, **prm)
+    return od, module, off, sim
+
+
+# ---------------------------------------------------------------------------------------
+def test_device_layout_is_bit_exact(oracle):
+    """'bit-exact stencil indices': the warp-sliced device layout decodes to exactly the
+    generator's (i, j) graph, diagonal first / ascending, and the transposed table points
+    at (j, i)."""
+    import ryujin_b200 as rj
+
+    for mesh in (make_mesh("sod2d", [37, 21]), make_mesh("sod3d", [9, 7, 5]), rj.CartesianMesh.forward_facing_step(0)):
+        od = rj.OfflineData.from_mesh(mesh)
+        host = od.host
+        so, rl, cols, tr = od.layout()
+        assert np.array_equal(rl, np.diff(host.row_starts.astype(np.int64)))
+        row_of_entry = np.full(od.n_entries_owned, -1, dtype=np.int64)
+        for i in range(host.n_owned):
+            base = int(so[i // 32]) + i % 32
+            e = base + 32 * np.arange(rl[i])
+            row_of_entry[e] = i
+            r0 = int(host.row_starts[i])
+            assert np.array_equal(cols[e], host.cols[r0 : r0 + rl[i]])
+            # transposed: entry (j, i)
+            assert np.array_equal(cols[tr[e]], np.full(rl[i], i))
+        for i in range(host.n_owned):
+            base = int(so[i // 32]) + i % 32
+            e = base + 32 * np.arange(rl[i])
+            assert np.array_equal(row_of_entry[tr[e]], cols[e].astype(np.int64))
+
+
+def test_interpolate_initial_values(oracle):
+    for case, n in (("sod2d", [16, 8]), ("vortex2d", [16, 16]), ("vortex3d", [8, 8, 4])):
+        od, module = make_product(case, n)
+        s = module.state_vector()
+        for t in (0.0, 0.37):
+            s.interpolate(t)
+            U = s.download()
+            ref = initial_state_host(oracle, case, od.host, t)
+            assert rel_linf(U, ref) < 5e-15, (case, t)
+
+
+@pytest.mark.parametrize("case,n_cells", [("sod2d", [48, 40]), ("vortex2d", [32, 32]), ("sod3d", [16, 8, 8]), ("vortex3d", [12, 12, 6])])
+def test_single_substep_parity(oracle, case, n_cells):
+    """prepare_state_vector + step<0>: every intermediate of the sweep against the oracle."""
+    od, module, off, sim = gpu_and_oracle(oracle, case, n_cells)
+    old, new = module.state_vector(), module.state_vector()
+    old.interpolate(0.0)
+    U0 = old.download()
+    sim.set_U(U0, 0)
+
+    t = 0.1
+    module.prepare_state_vector(old, t)
+    sim.prepare_state_vector(0, t)
+    assert rel_linf(old.download(), sim.get_U(0)) < 1e-15
+    assert np.max(rel_linf_per_component(old.download_precomputed(), sim.get_prec(0))) < 4e-15
+
+    module.cfl = 0.5
+    sim.set_cfl(0.5)
+    tau = module.step(old, [], [], new)
+    tau_ref = sim.step(0, [], [], 1)
+    assert abs(tau - tau_ref) <= 1e-14 * tau_ref
+
+    k = module.k
+    tol = 2e-13
+    assert np.max(np.abs(module.scratch("alpha") - sim.scratch("alpha"))) < tol
+    d_gpu, d_ref = module.scratch("dij"), sim.scratch("dij")
+    assert np.max(np.abs(d_gpu - d_ref)) <= 1e-14 * np.max(np.abs(d_ref))
+    assert np.max(rel_linf_per_component(module.scratch("r").reshape(-1, k), sim.scratch("r").reshape(-1, k))) < tol
+    assert np.max(rel_linf_per_component(module.scratch("bounds").reshape(-1, 3), sim.scratch("bounds").reshape(-1, 3))) < tol
+    p_gpu, p_ref = module.scratch("pij").reshape(-1, k), sim.scratch("pij").reshape(-1, k)
+    # skip diagonal entries: P_ii is written but never read (and not corrected in step 5)
+    diag = od.host.row_starts[:-1].astype(np.int64)
+    mask = np.ones(len(p_ref), dtype=bool)
+    mask[diag] = False
+    scale = np.max(np.abs(p_ref[mask]), axis=0)
+    assert np.max(np.abs(p_gpu[mask] - p_ref[mask]) / scale) < 1e-11  # P_ij is a difference of O(1) terms
+    for name in ("lij", "lij_next"):
+        a, b = module.scratch(name)[mask], sim.scratch(name)[mask]
+        assert np.max(np.abs(a - b)) < 1e-9, name
+        assert np.all((a >= 0.0) & (a <= 1.0))
+    assert rel_linf(new.download(), sim.get_U(1)) < 1e-13
+    assert (module.n_restarts(), module.n_warnings()) == sim.counters()
+
+
+@pytest.mark.parametrize("case,n_cells", [("sod2d", [40, 24]), ("vortex3d", [10, 10, 6])])
+def test_stage_weights_parity(oracle, case, n_cells):
+    """step<1> and step<2> with the ERK33 stage weights (time_integrator.template.h:373-403)."""
+    od, module, off, sim = gpu_and_oracle(oracle, case, n_cells)
+    S = [module.state_vector() for _ in range(4)]
+    S[0].interpolate(0.0)
+    sim.set_U(S[0].download(), 0)
+    module.cfl = 0.4
+    sim.set_cfl(0.4)
+    t = 0.0
+    module.prepare_state_vector(S[0], t)
+    sim.prepare_state_vector(0, t)
+    tau = module.step(S[0], [], [], S[1])
+    tau_ref = sim.step(0, [], [], 1)
+    assert abs(tau - tau_ref) <= 1e-14 * tau_ref
+    module.prepare_state_vector(S[1], t + tau)
+    sim.prepare_state_vector(1, t + tau_ref)
+    module.step(S[1], [S[0]], [-1.0], S[2], tau)
+    sim.step(1, [0], [-1.0], 2, tau_ref)
+    assert rel_linf(S[2].download(), sim.get_U(2)) < 1e-13
+    module.prepare_state_vector(S[2], t + 2 * tau)
+    sim.prepare_state_vector(2, t + 2 * tau_ref)
+    module.step(S[2], [S[0], S[1]], [0.75, -2.0], S[3], tau)
+    sim.step(2, [0, 1], [0.75, -2.0], 3, tau_ref)
+    assert rel_linf(S[3].download(), sim.get_U(3)) < 1e-13
+
+
+def run_cycles(module, sim, n_cycles, scheme_name, cfl_min=0.45, cfl_max=0.9, recovery="bang bang control"):
+    import ryujin_b200 as rj
+
+    scheme = {"erk 33": rj.TimeSteppingScheme.erk_33, "ssprk 33": rj.TimeSteppingScheme.ssprk_33,
+              "erk 11": rj.TimeSteppingScheme.erk_11, "erk 22": rj.TimeSteppingScheme.erk_22,
+              "erk 43": rj.TimeSteppingScheme.erk_43, "ssprk 22": rj.TimeSteppingScheme.ssprk_22}[scheme_name]
+    rec = rj.CFLRecoveryStrategy.none if recovery == "none" else rj.CFLRecoveryStrategy.bang_bang_control
+    ti = rj.TimeIntegrator(module, scheme, cfl_min, cfl_max, rec)
+    sim.configure_time_integrator(scheme_name, cfl_min, cfl_max, recovery)
+    state = module.state_vector()
+    state.interpolate(0.0)
+    sim.set_U(state.download(), 0)
+    t = t_ref = 0.0
+    taus, taus_ref = [], []
+    for _ in range(n_cycles):
+        tau = ti.step(state, t)
+        tau_ref = sim.time_step(t_ref)
+        taus.append(tau)
+        taus_ref.append(tau_ref)
+        t += tau
+        t_ref += tau_ref
+    return state, np.array(taus), np.array(taus_ref)
+
+
+def test_config1_sod_2d_256x256_100_cycles(oracle):
+    """BASELINE config 1: 2D Euler Sod shock tube, 256x256, 100 ERK33 cycles (= 300 forward
+    Euler updates); north_star tolerance 1e-12 relative L-infinity."""
+    od, module, off, sim = gpu_and_oracle(oracle, "sod2d", [256, 256])
+    assert od.host.n_owned == 257 * 257
+    state, taus, taus_ref = run_cycles(module, sim, 100, "erk 33")
+    assert np.max(np.abs(taus - taus_ref) / taus_ref) < 1e-13
+    err = rel_linf(state.download(), sim.get_U(0))
+    print("sod2d 100 cycles: rel Linf = %.3e" % err)
+    assert err < 1e-12
+    assert (module.n_restarts(), module.n_warnings()) == sim.counters()
+
+
+@pytest.mark.parametrize("scheme", ["ssprk 22", "ssprk 33", "erk 11", "erk 22", "erk 43"])
+def test_other_schemes(oracle, scheme):
+    od, module, off, sim = gpu_and_oracle(oracle, "sod2d", [64, 16])
+    state, taus, taus_ref = run_cycles(module, sim, 20, scheme)
+    assert np.max(np.abs(taus - taus_ref) / taus_ref) < 1e-13
+    assert rel_linf(state.download(), sim.get_U(0)) < 1e-12
+
+
+def test_vortex_3d_cycles(oracle):
+    """config 2 physics (3D isentropic vortex, time dependent Dirichlet data) at a size the
+    oracle finishes in seconds."""
+    od, module, off, sim = gpu_and_oracle(oracle, "vortex3d", [40, 40, 8])
+    state, taus, taus_ref = run_cycles(module, sim, 30, "erk 33", cfl_min=0.2, cfl_max=0.2, recovery="none")
+    assert np.max(np.abs(taus - taus_ref) / taus_ref) < 1e-13
+    err = rel_linf(state.download(), sim.get_U(0))
+    print("vortex3d 30 cycles: rel Linf = %.3e" % err)
+    assert err < 1e-12
+
+
+@pytest.mark.parametrize("scheme,key", [("erk 33", "erk33"), ("ssprk 33", "ssprk33")])
+@pytest.mark.parametrize("refinement", [5, 6])
+def test_reference_verification_goldens(oracle, scheme, key, refinement):
+    """The reference's own end-to-end goldens (tests/euler/verification-isentropic_vortex-2d-*.output)
+    reproduced by the CUDA path: final time and normalized Linf/L1/L2 errors."""
+    import ryujin_b200 as rj
+
+    g = load_golden("euler_verification.json")
+    ref = [r for r in g["runs"] if r["scheme"] == key and r["refinement"] == refinement][0]
+    n = 2**refinement
+    od, module = make_product("vortex2d", [n, n])
+    assert od.host.n_owned == ref["dofs"]
+    sch = rj.TimeSteppingScheme.erk_33 if key == "erk33" else rj.TimeSteppingScheme.ssprk_33
+    ti = rj.TimeIntegrator(module, sch, 0.2, 0.2, rj.CFLRecoveryStrategy.none)
+    state = module.state_vector()
+    state.interpolate(0.0)
+    t = 0.0
+    while t < 2.0:
+        t += ti.step(state, t)
+    assert abs(t - ref["t"]) <= 1e-13 * ref["t"], (t, ref["t"])
+    # error norms with the oracle's restatement of TimeLoop::compute_error on its own mesh
+    # (single rank: product numbering == lexicographic == oracle numbering)
+    from oracle import orc
+
+    off = oracle.assemble([n, n], [-5.0, -5.0], [10.0 / n, 10.0 / n], [orc.DIRICHLET] * 4)
+    sim = off.euler_sim(kind=orc.ISENTROPIC_VORTEX, direction=(1.0, 1.0), position=(-1.0, -1.0), mach=1.0, beta=5.0)
+    sim.set_U(state.download(), 0)
+    err = sim.errors(t)
+    for name in ("Linf", "L1", "L2"):
+        assert abs(err[name] - ref[name]) <= 1e-9 * ref[name], (name, err[name], ref[name])
+
+
+def test_restart_and_warning_semantics(oracle):
+    """IDViolationStrategy (hyperbolic_module.template.h:1190-1210): an over-aggressive CFL
+    makes the low-order update leave the bounds; raise_exception -> Restart + n_restarts,
+    warn -> n_warnings; the bang-bang TimeIntegrator recovers at cfl_min exactly like the
+    oracle's."""
+    import ryujin_b200 as rj
+
+    od, module, off, sim = gpu_and_oracle(oracle, "sod2d", [64, 8])
+    old, new = module.state_vector(), module.state_vector()
+    old.interpolate(0.0)
+    sim.set_U(old.download(), 0)
+    module.prepare_state_vector(old, 0.0)
+    sim.prepare_state_vector(0, 0.0)
+    module.cfl = 4.0
+    sim.set_cfl(4.0)
+    module.id_violation_strategy = rj.IDViolationStrategy.warn
+    sim.set_raise_on_violation(False)
+    module.step(old, [], [], new)
+    sim.step(0, [], [], 1)
+    assert (module.n_restarts(), module.n_warnings()) == sim.counters() == (0, 1)
+    module.id_violation_strategy = rj.IDViolationStrategy.raise_exception
+    sim.set_raise_on_violation(True)
+    with pytest.raises(rj.Restart):
+        module.step(old, [], [], new)
+    from oracle import orc
+
+    with pytest.raises(orc.Restart):
+        sim.step(0, [], [], 1)
+    assert (module.n_restarts(), module.n_warnings()) == sim.counters() == (1, 1)
+
+    # bang-bang recovery through the TimeIntegrator
+    od2, module2, off2, sim2 = gpu_and_oracle(oracle, "sod2d", [64, 8])
+    state, taus, taus_ref = run_cycles(module2, sim2, 10, "erk 33", cfl_min=0.3, cfl_max=3.0)
+    assert np.max(np.abs(taus - taus_ref) / taus_ref) < 1e-13
+    assert (module2.n_restarts(), module2.n_warnings()) == sim2.counters()
+    assert module2.n_restarts() > 0
+    assert rel_linf(state.download(), sim2.get_U(0)) < 1e-12
+
+
+def test_limiter_iterations_and_parameters(oracle):
+    """non default module parameters travel through the ABI: 1 limiter iteration, evc factor,
+    Riemann solver Newton iterations."""
+    for mp, prm in (
+        (dict(limiter_iterations=1), dict(limiter_iterations=1)),
+        (dict(limiter_iterations=0), dict(limiter_iterations=0)),
+        (dict(indicator_evc_factor=0.5, riemann_newton_max_iterations=2),
+         dict(indicator_evc_factor=0.5, riemann_newton_max_iterations=2)),
+        (dict(limiter_relaxation_factor=2.0, limiter_newton_max_iterations=4),
+         dict(limiter_relaxation_factor=2.0, limiter_newton_max_iterations=4)),
+    ):
+        od, module = make_product("sod2d", [32, 8], module_params=mp)
+        off, sim = make_oracle(oracle, "sod2d", od.host, **prm)
+        state, taus, taus_ref = run_cycles(module, sim, 10, "erk 33")
+        assert np.max(np.abs(taus - taus_ref) / taus_ref) < 1e-13, mp
+        assert rel_linf(state.download(), sim.get_U(0)) < 1e-12, mp
+
+
+def test_gamma_parameter(oracle):
+    od, module = make_product("sod2d", [32, 8], gamma=5.0 / 3.0)
+    off, sim = make_oracle(oracle, "sod2d", od.host, gamma=5.0 / 3.0)
+    # the numpy initial state helper assumes 1.4; take the device's interpolation instead
+    state, taus, taus_ref = run_cycles(module, sim, 10, "erk 33")
+    assert np.max(np.abs(taus - taus_ref) / taus_ref) < 1e-13
+    assert rel_linf(state.download(), sim.get_U(0)) < 1e-12
+
+
+def test_forward_facing_step_config3(oracle):
+    """BASELINE config 3 topology (Mach 3 flow over a step; irregular rows) against the oracle."""
+    import ryujin_b200 as rj
+    from helpers import oracle_offline_from_host
+    from oracle import orc
+
+    mesh = rj.CartesianMesh.forward_facing_step(refinement=2)
+    od = rj.OfflineData.from_mesh(mesh)
+    module = rj.HyperbolicModule(od, rj.HyperbolicSystem(), rj.InitialValues(rj.InitialState.uniform, primitive=[1.4, 3.0, 1.0]))
+    off = oracle_offline_from_host(oracle, od.host)
+    sim = off.euler_sim(kind=orc.UNIFORM, primitive=(1.4, 3.0, 1.0))
+    state, taus, taus_ref = run_cycles(module, sim, 60, "erk 33")
+    assert np.max(np.abs(taus - taus_ref) / taus_ref) < 1e-13
+    err = rel_linf(state.download(), sim.get_U(0))
+    print("step: rel Linf = %.3e" % err)
+    assert err < 1e-12
+    assert (module.n_restarts(), module.n_warnings()) == sim.counters()
+
+
+def test_conservation_and_symmetry_properties():
+    """Size independent properties at a size the oracle is not run at: closed slip box =>
+    total mass and energy are conserved to round-off; d_ij is bitwise symmetric; 0 <= alpha,
+    l_ij <= 1."""
+    import ryujin_b200 as rj
+
+    B = rj.Boundary
+    mesh = rj.CartesianMesh([96, 96, 48], [0.0, 0.0, 0.0], [1.0, 1.0, 0.5], [B.slip] * 6)
+    od = rj.OfflineData.from_mesh(mesh)
+    module = rj.HyperbolicModule(
+        od, rj.HyperbolicSystem(),
+        rj.InitialValues(rj.InitialState.contrast, direction=[1.0, 1.0, 0.5], position=[0.4, 0.4, 0.2],
+                         primitive=[1.0, 0.0, 1.0], primitive_right=[0.125, 0.0, 0.1]),
+    )
+    ti = rj.TimeIntegrator(module)
+    state = module.state_vector()
+    state.interpolate(0.0)
+    m = od.host.mi[: od.host.n_owned]
+    U0 = state.download()
+    t = 0.0
+    for _ in range(10):
+        t += ti.step(state, t)
+    U1 = state.download()
+    assert np.all(np.isfinite(U1))
+    for c in (0, 4):
+        q0, q1 = np.dot(m, U0[:, c]), np.dot(m, U1[:, c])
+        assert abs(q1 - q0) <= 1e-12 * abs(q0), (c, q0, q1)
+    d = module.scratch("dij")
+    host = od.host
+    rows = np.repeat(np.arange(host.n_owned), np.diff(host.row_starts.astype(np.int64)))
+    cols = host.cols.astype(np.int64)
+    key = rows * host.n_owned + cols
+    keyT = cols * host.n_owned + rows
+    order = np.argsort(key)
+    pos = np.searchsorted(key[order], keyT)
+    dT = d[order][pos]
+    assert np.array_equal(d, dT)
+    alpha = module.scratch("alpha")
+    assert np.all((alpha >= 0.0) & (alpha <= 1.0))
+    off_diag = rows != cols
+    for name in ("lij", "lij_next"):
+        l = module.scratch(name)[off_diag]
+        assert np.all((l >= 0.0) & (l <= 1.0))
+    assert module.kernel_launches() > 0
