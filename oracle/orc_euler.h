@@ -258,9 +258,10 @@ namespace orc
         const double p = pressure(U);
         const double s = p / orc::pow(rho, gamma);
 
+        const double rho_inverse = 1. / rho; /* m / rho: Tensor / scalar */
         Vec<dim> vperp;
         for (int d = 0; d < dim; ++d)
-          vperp[d] = m[d] / rho - vn * normal[d];
+          vperp[d] = m[d] * rho_inverse - vn * normal[d];
 
         const double vn_new = 0.5 * (R_1 + R_2);
 

@@ -259,9 +259,11 @@ namespace orc
               continue;
 
             const double nrm = norm<dim>(c_ij);
+            /* Tensor / scalar multiplies by the rounded inverse (dealii::Tensor::operator/=) */
+            const double nrm_inverse = 1. / nrm;
             Vec<dim> n_ij;
             for (int d = 0; d < dim; ++d)
-              n_ij[d] = c_ij[d] / nrm;
+              n_ij[d] = c_ij[d] * nrm_inverse;
             const double lambda_max = riemann_solver.compute(U_i, U_j, n_ij);
             dij_[e] = nrm * lambda_max;
           }
@@ -284,9 +286,10 @@ namespace orc
           const std::size_t e = od_.row_ptr[i] + col_idx;
           const auto c_ji = od_.c(od_.transposed[e]);
           const double norm_ji = norm<dim>(c_ji);
+          const double norm_ji_inverse = 1. / norm_ji;
           Vec<dim> n_ji;
           for (int d = 0; d < dim; ++d)
-            n_ji[d] = c_ji[d] / norm_ji;
+            n_ji[d] = c_ji[d] * norm_ji_inverse;
           const double d_ij = dij_[e];
           const double lambda_max = riemann_solver.compute(U_j, U_i, n_ji);
           const double d_ji = norm_ji * lambda_max;
@@ -379,9 +382,9 @@ namespace orc
               const double regularization = 100. * min_double;
               Vec<dim> scaled_c_ij;
               {
-                const double div = std::max(d_ij, regularization);
+                const double inverse = 1. / std::max(d_ij, regularization);
                 for (int d = 0; d < dim; ++d)
-                  scaled_c_ij[d] = c_ij[d] / div;
+                  scaled_c_ij[d] = c_ij[d] * inverse;
               }
 
               const auto flux_j = sys_.f(U_j);

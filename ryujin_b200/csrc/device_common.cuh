@@ -4,6 +4,7 @@
 #pragma once
 
 #include "../../include/ryujin_b200.h"
+#include "accurate_pow.h"
 
 #include <cfloat>
 #include <cstdint>

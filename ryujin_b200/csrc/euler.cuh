@@ -58,7 +58,7 @@ namespace rjb
     RJ_DEVICE static double specific_entropy(const Params &p, const double (&U)[k])
     {
       const double rho_inverse = 1. / U[0];
-      return internal_energy(U) * pow(rho_inverse, p.gamma);
+      return internal_energy(U) * rj_pow(rho_inverse, p.gamma);
     }
 
     RJ_DEVICE static double harten_entropy(const Params &p, const double (&U)[k])
@@ -68,7 +68,7 @@ namespace rjb
       for (int d = 1; d < dim; ++d)
         m2 += U[1 + d] * U[1 + d];
       const double rho_rho_e = U[0] * U[dim + 1] - 0.5 * m2;
-      return pow(rho_rho_e, p.gamma_plus_one_inverse);
+      return rj_pow(rho_rho_e, p.gamma_plus_one_inverse);
     }
 
     /* precomputation_loop body, hyperbolic_system.h:732-735 */
@@ -87,7 +87,7 @@ namespace rjb
         m2 += U[1 + d] * U[1 + d];
       const double rho_rho_e = U[0] * U[dim + 1] - 0.5 * m2;
       const double factor =
-          p.gamma_plus_one_inverse * pow(rho_rho_e, -p.gamma * p.gamma_plus_one_inverse);
+          p.gamma_plus_one_inverse * rj_pow(rho_rho_e, -p.gamma * p.gamma_plus_one_inverse);
       result[0] = factor * U[dim + 1];
 #pragma unroll
       for (int d = 0; d < dim; ++d)
@@ -115,24 +115,24 @@ namespace rjb
       return f;
     }
 
-    /* f(U) . c, cf. f() at hyperbolic_system.h:1164-1181 */
-    RJ_DEVICE static void
-    flux_dot(const double (&U)[k], const Flux &f, const double (&c)[dim], double (&out)[k])
+    /* Element (comp, d) of the flux tensor f(U), hyperbolic_system.h:1164-1181,
+     * rebuilt from (U, 1/rho, p) with the reference's operation order:
+     *   f[0] = m;  f[1+i] = m * (m[i] * rho_inverse), f[1+i][i] += p;
+     *   f[dim+1] = m * (rho_inverse * (E + p)).
+     * comp and d are compile time constants after unrolling. */
+    RJ_DEVICE static double f_element(const double (&U)[k], const Flux &f, const int comp, const int d)
     {
-      double mc = U[1] * c[0];
-#pragma unroll
-      for (int d = 1; d < dim; ++d)
-        mc += U[1 + d] * c[d];
-      const double vc = mc * f.rho_inverse;
-      out[0] = mc;
-#pragma unroll
-      for (int d = 0; d < dim; ++d)
-        out[1 + d] = U[1 + d] * vc + f.p * c[d];
-      out[dim + 1] = vc * (U[dim + 1] + f.p);
+      if (comp == 0)
+        return U[1 + d];
+      if (comp == dim + 1)
+        return U[1 + d] * (f.rho_inverse * (U[dim + 1] + f.p));
+      const double v = U[1 + d] * (U[comp] * f.rho_inverse);
+      return (d == comp - 1) ? v + f.p : v;
     }
 
-    /* flux_divergence(flux_i, flux_j, c_ij) = -(f_i + f_j) . c_ij,
-     * hyperbolic_system.h:1210-1216 */
+    /* flux_divergence(flux_i, flux_j, c_ij) = -contract(add(flux_i, flux_j), c_ij),
+     * hyperbolic_system.h:1210-1216, convenience_macros.h:75-96: per component
+     * the sum over d runs in ascending order on the added tensors. */
     RJ_DEVICE static void flux_divergence(const double (&U_i)[k],
                                           const Flux &f_i,
                                           const double (&U_j)[k],
@@ -140,12 +140,14 @@ namespace rjb
                                           const double (&c)[dim],
                                           double (&out)[k])
     {
-      double a[k], b[k];
-      flux_dot(U_i, f_i, c, a);
-      flux_dot(U_j, f_j, c, b);
 #pragma unroll
-      for (int q = 0; q < k; ++q)
-        out[q] = -(a[q] + b[q]);
+      for (int q = 0; q < k; ++q) {
+        double s = (f_element(U_i, f_i, q, 0) + f_element(U_j, f_j, q, 0)) * c[0];
+#pragma unroll
+        for (int d = 1; d < dim; ++d)
+          s += (f_element(U_i, f_i, q, d) + f_element(U_j, f_j, q, d)) * c[d];
+        out[q] = -s;
+      }
     }
 
     RJ_DEVICE static double filter_vacuum_density(const Params &p, const double rho)
@@ -188,20 +190,21 @@ namespace rjb
       const double R_2 = component == 2 ? vn_bar + 2. * a_bar / (gamma - 1.) : vn + 2. * a / (gamma - 1.);
 
       const double pr = pressure(p, U);
-      const double s = pr / pow(rho, gamma);
+      const double s = pr / rj_pow(rho, gamma);
 
+      const double rho_inverse = 1. / rho; /* m / rho: Tensor / scalar multiplies by the inverse */
       double vperp[dim];
       double vperp2 = 0.;
 #pragma unroll
       for (int d = 0; d < dim; ++d) {
-        vperp[d] = U[1 + d] / rho - vn * normal[d];
+        vperp[d] = U[1 + d] * rho_inverse - vn * normal[d];
         vperp2 += vperp[d] * vperp[d];
       }
       const double vn_new = 0.5 * (R_1 + R_2);
       const double tmp = ((gamma - 1.) / 4.) * (R_2 - R_1);
       double rho_new = 1. / (gamma * s) * (tmp * tmp);
-      rho_new = pow(rho_new, 1. / (gamma - 1.));
-      const double p_new = s * pow(rho_new, gamma);
+      rho_new = rj_pow(rho_new, 1. / (gamma - 1.));
+      const double p_new = s * rj_pow(rho_new, gamma);
 
       U_new[0] = rho_new;
 #pragma unroll
@@ -302,7 +305,7 @@ namespace rjb
       const double radicand = Az / (p_star + Bz);
       const double true_value = (p_star - rd.p) * sqrt(radicand);
       const double exponent = 0.5 * (gamma - 1.) / gamma;
-      const double factor = pow(p_star / rd.p, exponent) - 1.;
+      const double factor = rj_pow(p_star / rd.p, exponent) - 1.;
       const double false_value = 2. * rd.a * factor / (gamma - 1.);
       return p_star >= rd.p ? true_value : false_value;
     }
@@ -315,7 +318,7 @@ namespace rjb
       const double true_value =
           (denominator - 0.5 * (p_star - rd.p)) / (denominator * sqrt(radicand_inverse));
       const double exponent = (-1. - gamma) * 0.5 * p.gamma_inverse;
-      const double factor = (gamma - 1.) * 0.5 * p.gamma_inverse * pow(p_star / rd.p, exponent) / rd.p;
+      const double factor = (gamma - 1.) * 0.5 * p.gamma_inverse * rj_pow(p_star / rd.p, exponent) / rd.p;
       const double false_value = factor * 2. * rd.a * p.gamma_minus_one_inverse;
       return p_star >= rd.p ? true_value : false_value;
     }
@@ -352,9 +355,9 @@ namespace rjb
         const double factor = (gamma - 1.) * 0.5;
         const double numerator = positive_part(rd_i.a + rd_j.a - factor * (rd_j.u - rd_i.u));
         const double denominator =
-            rd_i.a * pow(rd_i.p * inv_p_j, -factor * p.gamma_inverse) + rd_j.a;
+            rd_i.a * rj_pow(rd_i.p * inv_p_j, -factor * p.gamma_inverse) + rd_j.a;
         const double exponent = 2.0 * gamma * p.gamma_minus_one_inverse;
-        rarefaction = rd_j.p * pow(numerator / denominator, exponent);
+        rarefaction = rd_j.p * rj_pow(numerator / denominator, exponent);
       }
 
       /* p_star_failsafe, :332-374; radicand_inverse terms shared with
@@ -458,14 +461,19 @@ namespace rjb
         Flux fi;
         fi.rho_inverse = rho_i_inverse;
         fi.p = p_i;
-        double a[k], b[k];
-        flux_dot(U_j, fj, c_ij, a);
-        flux_dot(U_i, fi, c_ij, b);
-        /* a[0] = m_j . c_ij */
-        left += (eta_j * fj.rho_inverse - eta_i * rho_i_inverse) * a[0];
+        double mjc = U_j[1] * c_ij[0];
 #pragma unroll
-        for (int q = 0; q < k; ++q)
-          right[q] += a[q] - b[q];
+        for (int d = 1; d < dim; ++d)
+          mjc += U_j[1 + d] * c_ij[d];
+        left += (eta_j * fj.rho_inverse - eta_i * rho_i_inverse) * mjc;
+#pragma unroll
+        for (int q = 0; q < k; ++q) {
+          double s = (f_element(U_j, fj, q, 0) - f_element(U_i, fi, q, 0)) * c_ij[0];
+#pragma unroll
+          for (int d = 1; d < dim; ++d)
+            s += (f_element(U_j, fj, q, d) - f_element(U_i, fi, q, d)) * c_ij[d];
+          right[q] += s;
+        }
       }
 
       RJ_DEVICE double alpha(const Params &p, const double hd_i) const
@@ -590,7 +598,7 @@ namespace rjb
         for (int q = 0; q < k; ++q)
           U_r[q] = U[q] + t_r * P[q];
         const double rho_r = U_r[0];
-        const double rho_r_gamma = pow(rho_r, gamma);
+        const double rho_r_gamma = rj_pow(rho_r, gamma);
         const double rho_e_r = internal_energy(U_r);
         const double psi_r = relax_small * rho_r * rho_e_r - s_min * rho_r * rho_r_gamma;
 
@@ -603,7 +611,7 @@ namespace rjb
         for (int q = 0; q < k; ++q)
           U_l[q] = U[q] + t_l * P[q];
         const double rho_l = U_l[0];
-        const double rho_l_gamma = pow(rho_l, gamma);
+        const double rho_l_gamma = rj_pow(rho_l, gamma);
         const double rho_e_l = internal_energy(U_l);
         const double psi_l = relax_small * rho_l * rho_e_l - s_min * rho_l * rho_l_gamma;
 
@@ -682,8 +690,8 @@ namespace rjb
         const double T = 1. - (gamma - 1.) / (2. * gamma) * factor * factor;
         const double u = iv.mach_number - factor * pb1;
         const double v = factor * pb0;
-        const double rho = pow(T, 1. / (gamma - 1.));
-        const double pr = pow(rho, gamma);
+        const double rho = rj_pow(T, 1. / (gamma - 1.));
+        const double pr = rj_pow(rho, gamma);
         const double E = pr / (gamma - 1.) + 0.5 * rho * (u * u + v * v);
 #pragma unroll
         for (int q = 0; q < k; ++q)

@@ -66,6 +66,7 @@ struct rj_comm {
 
 struct rj_state {
   rj_hyperbolic_module *hm = nullptr;
+  int device = 0; /* destruction must not depend on the module still being alive */
   double *U = nullptr;    /* k * ld */
   double *prec = nullptr; /* n_prec * ld */
 };
@@ -74,6 +75,7 @@ struct rj_state {
 
 struct rj_hyperbolic_module {
   const rj_offline *od = nullptr;
+  int device = 0;
   rj_comm *comm = nullptr;
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
@@ -162,9 +164,59 @@ struct rj_hyperbolic_module {
     if (n_threads == 0)
       return;
     const unsigned int grid = (unsigned int)((n_threads + block - 1) / block);
-    kernel<<<grid, block, 0, stream>>>(args...);
+    if (profiling) {
+      /* per-kernel device time on the launching stream (bench.py roofline) */
+      if (prof_used + 2 > prof_events.size()) {
+        prof_events.resize(prof_used + 2);
+        RJ_CUDA(cudaEventCreate(&prof_events[prof_used]));
+        RJ_CUDA(cudaEventCreate(&prof_events[prof_used + 1]));
+      }
+      RJ_CUDA(cudaEventRecord(prof_events[prof_used], stream));
+      kernel<<<grid, block, 0, stream>>>(args...);
+      RJ_CUDA(cudaEventRecord(prof_events[prof_used + 1], stream));
+      prof_slots.push_back(prof_slot);
+      prof_used += 2;
+    } else
+      kernel<<<grid, block, 0, stream>>>(args...);
     RJ_CUDA(cudaGetLastError());
     ++launches;
+  }
+
+  /* profiling: slots name the kernels of one update */
+  enum ProfSlot {
+    P_BC = 0,
+    P_PRECOMPUTE,
+    P_DIJ_ALPHA,
+    P_BOUNDARY_DIJ,
+    P_DII_TAU,
+    P_LOW_ORDER,
+    P_PIJ_LIJ,
+    P_HIGH_ORDER_NEXT,
+    P_HIGH_ORDER_FINAL,
+    P_OTHER,
+    P_N_SLOTS
+  };
+  bool profiling = false;
+  int prof_slot = P_OTHER;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<int> prof_slots;
+  size_t prof_used = 0;
+  double prof_ms[P_N_SLOTS] = {};
+  uint64_t prof_count[P_N_SLOTS] = {};
+
+  void tag(int slot) { prof_slot = slot; }
+
+  /* call after a stream synchronize */
+  void collect_profile()
+  {
+    for (size_t n = 0; n < prof_slots.size(); ++n) {
+      float ms = 0.f;
+      RJ_CUDA(cudaEventElapsedTime(&ms, prof_events[2 * n], prof_events[2 * n + 1]));
+      prof_ms[prof_slots[n]] += ms;
+      prof_count[prof_slots[n]]++;
+    }
+    prof_slots.clear();
+    prof_used = 0;
   }
 
   /* -------- ghost exchanges (NCCL send/recv groups, cf.
@@ -251,8 +303,8 @@ struct rj_hyperbolic_module {
 
 rj_hyperbolic_module::~rj_hyperbolic_module()
 {
-  if (od)
-    cudaSetDevice(od->device);
+  /* garbage collected hosts may destroy the offline data first: do not touch od */
+  cudaSetDevice(device);
   auto f = [](void *p) {
     if (p)
       cudaFree(p);
@@ -268,6 +320,8 @@ rj_hyperbolic_module::~rj_hyperbolic_module()
   f(send_buffer);
   f(staging);
   f(csr_to_sliced);
+  for (auto ev : prof_events)
+    cudaEventDestroy(ev);
   if (h_scalars)
     cudaFreeHost(h_scalars);
   if (owns_stream && stream)
@@ -357,6 +411,7 @@ namespace rjb
     {
       RJ_CUDA(cudaSetDevice(od->device));
       const StencilView v = view();
+      tag(P_BC);
       launch(k_apply_boundary_conditions<Eq, InitialValuesDevice>,
              od->n_bgroups,
              128,
@@ -371,8 +426,11 @@ namespace rjb
              iv,
              t,
              state.U);
+      tag(P_OTHER);
       exchange_vector(state.U, Eq::k); /* C1 */
+      tag(P_PRECOMPUTE);
       launch_rows(k_precompute<Eq>, 0, od->n_owned, v, prm, 0u, od->n_owned, state.U, state.prec);
+      tag(P_OTHER);
       exchange_vector(state.prec, Eq::n_prec); /* C2 */
     }
 
@@ -425,13 +483,17 @@ namespace rjb
       const StencilView v = view();
       const uint32_t n_owned = od->n_owned;
 
+      tag(P_OTHER);
       launch(k_reset_scalars, 1, 1, scalars);
 
       /* Step 2: d_ij (j > i), alpha_i; then C3 */
+      tag(P_DIJ_ALPHA);
       launch_rows(k_dij_alpha<Eq>, 0, n_owned, v, prm, 0u, n_owned, old_state.U, old_state.prec, dij, alpha);
+      tag(P_OTHER);
       exchange_vector(alpha, 1);
 
       /* Step 3: boundary d_ij, d_ii, tau_max; C4 */
+      tag(P_BOUNDARY_DIJ);
       launch(k_boundary_dij<Eq>,
              od->n_pairs,
              128,
@@ -447,7 +509,9 @@ namespace rjb
              old_state.U,
              old_state.prec,
              dij);
+      tag(P_DII_TAU);
       launch_rows(k_dii_tau, 0, n_owned, v, 0u, n_owned, cfl, dij, scalars);
+      tag(P_OTHER);
       launch(k_tau_local, 1, 1, scalars, tau_max_in);
       if (comm && comm->n_ranks > 1)
         RJ_NCCL(ncclAllReduce(
@@ -455,6 +519,7 @@ namespace rjb
       launch(k_tau_finalize, 1, 1, scalars, tau);
 
       /* Step 4: low-order update, bounds, r_i, P_ij; C6 */
+      tag(P_LOW_ORDER);
       switch (stages) {
       case 0: low_order<0>(old_state, stage_states, stage_weights, new_state); break;
       case 1: low_order<1>(old_state, stage_states, stage_weights, new_state); break;
@@ -462,12 +527,15 @@ namespace rjb
       case 3: low_order<3>(old_state, stage_states, stage_weights, new_state); break;
       case 4: low_order<4>(old_state, stage_states, stage_weights, new_state); break;
       }
+      tag(P_OTHER);
       exchange_vector(r, Eq::k);
 
       /* Step 5: P_ij correction and first l_ij; C7 */
       const unsigned int n_iterations = mp.limiter_iterations;
       if (n_iterations != 0) {
+        tag(P_PIJ_LIJ);
         launch_rows(k_pij_lij<Eq>, 0, n_owned, v, prm, 0u, n_owned, new_state.U, r, bounds, scalars, pij, lij);
+        tag(P_OTHER);
         exchange_matrix(lij);
       }
 
@@ -476,10 +544,12 @@ namespace rjb
         const bool last_round = (pass + 1 == n_iterations);
         if ((n_iterations == 2) && last_round)
           std::swap(lij, lij_next);
+        tag(last_round ? P_HIGH_ORDER_FINAL : P_HIGH_ORDER_NEXT);
         if (last_round)
           launch_rows(k_high_order<Eq, true>, 0, n_owned, v, prm, 0u, n_owned, bounds, pij, lij, lij_next, new_state.U);
         else {
           launch_rows(k_high_order<Eq, false>, 0, n_owned, v, prm, 0u, n_owned, bounds, pij, lij, lij_next, new_state.U);
+          tag(P_OTHER);
           exchange_matrix(lij_next);
         }
       }
@@ -495,6 +565,8 @@ namespace rjb
                               stream));
       RJ_CUDA(cudaMemcpyAsync(h_scalars, scalars, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
       RJ_CUDA(cudaStreamSynchronize(stream));
+      if (profiling)
+        collect_profile();
 
       if (h_scalars->numeric_error)
         throw NumericError("I'm sorry, Dave. I'm afraid I can't do that.\nWe crashed. "
@@ -818,6 +890,7 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
       throw InvalidArgument("rj_hyperbolic_module_create: equation module not available");
 
     hm->od = od;
+    hm->device = od->device;
     hm->comm = comm;
     hm->eq = *eq;
     hm->mp = *mp;
@@ -948,6 +1021,43 @@ int rj_hyperbolic_module_sizes(const rj_hyperbolic_module *hm, uint64_t out[6])
 
 uint64_t rj_hyperbolic_module_kernel_launches(const rj_hyperbolic_module *hm) { return hm->launches; }
 
+int rj_hyperbolic_module_set_profiling(rj_hyperbolic_module *hm, int on)
+{
+  return guarded([&] {
+    if (!hm)
+      throw InvalidArgument("null argument");
+    RJ_CUDA(cudaSetDevice(hm->device));
+    RJ_CUDA(cudaStreamSynchronize(hm->stream));
+    if (hm->profiling)
+      hm->collect_profile();
+    hm->profiling = on != 0;
+    if (on)
+      for (int q = 0; q < rj_hyperbolic_module::P_N_SLOTS; ++q) {
+        hm->prof_ms[q] = 0.;
+        hm->prof_count[q] = 0;
+      }
+    return RJ_OK;
+  });
+}
+
+int rj_hyperbolic_module_get_profile(rj_hyperbolic_module *hm, double ms[RJ_N_PROFILE_SLOTS], uint64_t counts[RJ_N_PROFILE_SLOTS])
+{
+  return guarded([&] {
+    if (!hm)
+      throw InvalidArgument("null argument");
+    static_assert(RJ_N_PROFILE_SLOTS == rj_hyperbolic_module::P_N_SLOTS, "profile slots");
+    RJ_CUDA(cudaSetDevice(hm->device));
+    RJ_CUDA(cudaStreamSynchronize(hm->stream));
+    if (hm->profiling)
+      hm->collect_profile();
+    for (int q = 0; q < RJ_N_PROFILE_SLOTS; ++q) {
+      ms[q] = hm->prof_ms[q];
+      counts[q] = hm->prof_count[q];
+    }
+    return RJ_OK;
+  });
+}
+
 int rj_hyperbolic_module_get_scratch(rj_hyperbolic_module *hm, int what, double *host_out)
 {
   return guarded([&] {
@@ -1000,6 +1110,7 @@ int rj_state_create(rj_state **out, rj_hyperbolic_module *hm)
     RJ_CUDA(cudaSetDevice(hm->od->device));
     auto s = std::unique_ptr<rj_state>(new rj_state());
     s->hm = hm;
+    s->device = hm->od->device;
     const size_t ld = hm->od->ld;
     RJ_CUDA(cudaMalloc(&s->U, size_t(hm->k) * ld * sizeof(double)));
     RJ_CUDA(cudaMalloc(&s->prec, size_t(hm->n_prec) * ld * sizeof(double)));
@@ -1015,7 +1126,7 @@ void rj_state_destroy(rj_state *s)
 {
   if (!s)
     return;
-  cudaSetDevice(s->hm->od->device);
+  cudaSetDevice(s->device);
   cudaFree(s->U);
   cudaFree(s->prec);
   delete s;

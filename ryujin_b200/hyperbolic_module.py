@@ -281,6 +281,20 @@ class HyperbolicModule:
     def kernel_launches(self):
         return int(lib.rj_hyperbolic_module_kernel_launches(self._h))
 
+    PROFILE_SLOTS = ("boundary_conditions", "precompute", "dij_alpha", "boundary_dij", "dii_tau", "low_order",
+                     "pij_lij", "high_order_next_lij", "high_order_final", "plumbing")
+
+    def set_profiling(self, on):
+        """per-kernel CUDA-event timing on the module's stream (bench.py roofline)"""
+        check(lib.rj_hyperbolic_module_set_profiling(self._h, int(bool(on))))
+
+    def profile(self):
+        """{kernel: (total_ms, launches)} accumulated since set_profiling(True)"""
+        ms = (C.c_double * len(self.PROFILE_SLOTS))()
+        cnt = (C.c_uint64 * len(self.PROFILE_SLOTS))()
+        check(lib.rj_hyperbolic_module_get_profile(self._h, ms, cnt))
+        return {name: (ms[q], int(cnt[q])) for q, name in enumerate(self.PROFILE_SLOTS)}
+
     def scratch(self, name):
         """alpha / dij / lij / lij_next / pij / r / bounds as host arrays in the
         host's CSR entry order (parity tests)."""
