@@ -167,6 +167,20 @@ typedef struct rj_offline rj_offline; /* device resident stencil data */
 int rj_offline_create(rj_offline **out, const rj_offline_desc *desc, int device);
 void rj_offline_destroy(rj_offline *od);
 
+/* Host-only variant: computes the same layout and exchange lists without touching
+ * CUDA (no device arrays; cannot be used to create a module).  For tests of the
+ * host logic on CPU boxes. */
+int rj_offline_create_host_layout(rj_offline **out, const rj_offline_desc *desc);
+/* sizes = {n_neighbors, n_send_rows, n_mat_send} */
+int rj_offline_exchange_sizes(const rj_offline *od, uint64_t sizes[3]);
+/* neighbor_info: 9 values per neighbour {rank, ghost_start, ghost_count, send_offset,
+ * send_count, mat_send_offset, mat_send_count, mat_recv_offset, mat_recv_count};
+ * send_rows: local rows packed for the vector exchanges; mat_send_entries: device-layout
+ * entry indices packed for the matrix ghost-row exchanges (cf. entries_to_be_sent,
+ * sparse_matrix_simd.template.h:214-266); the receiver stores them contiguously at
+ * entry index mat_recv_offset (cf. receive_targets, :164-188). */
+int rj_offline_exchange_get(const rj_offline *od, uint32_t *neighbor_info, uint32_t *send_rows, uint32_t *mat_send_entries);
+
 /* Device layout introspection for parity tests ("bit-exact stencil indices"):
  * sizes = {n_slices, n_entries_owned, n_entries_total, ld (vector stride)} */
 int rj_offline_layout_sizes(const rj_offline *od, uint64_t sizes[4]);

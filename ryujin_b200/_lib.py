@@ -130,6 +130,9 @@ _SIGNATURES = {
     "rj_version": (C.c_char_p, []),
     "rj_offline_create": (C.c_int, [C.POINTER(vp), C.POINTER(OfflineDesc), C.c_int]),
     "rj_offline_destroy": (None, [vp]),
+    "rj_offline_create_host_layout": (C.c_int, [C.POINTER(vp), C.POINTER(OfflineDesc)]),
+    "rj_offline_exchange_sizes": (C.c_int, [vp, u64p]),
+    "rj_offline_exchange_get": (C.c_int, [vp, u32p, u32p, u32p]),
     "rj_offline_layout_sizes": (C.c_int, [vp, u64p]),
     "rj_offline_layout_get": (C.c_int, [vp, u64p, u32p, u32p, u32p]),
     "rj_mesh_generate": (C.c_int, [C.POINTER(vp), C.POINTER(MeshDesc), C.c_int, C.c_int]),

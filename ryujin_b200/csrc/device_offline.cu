@@ -12,6 +12,8 @@
 
 rj_offline::~rj_offline()
 {
+  if (host_only)
+    return; /* no device allocations were made */
   auto f = [](void *p) {
     if (p)
       cudaFree(p);
@@ -44,11 +46,14 @@ namespace rjb
 {
   namespace
   {
+    /* host_only: keep host mirrors, touch no CUDA API (layout tests on CPU boxes) */
+    bool g_host_only = false;
+
     template <typename T>
     T *upload(const std::vector<T> &h)
     {
       T *d = nullptr;
-      if (h.empty())
+      if (h.empty() || g_host_only)
         return d;
       RJ_CUDA(cudaMalloc(&d, h.size() * sizeof(T)));
       RJ_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -57,8 +62,9 @@ namespace rjb
   } // namespace
 
 
-  rj_offline *build_device_offline(const rj_offline_desc &d, int device)
+  rj_offline *build_device_offline(const rj_offline_desc &d, int device, bool host_only)
   {
+    g_host_only = host_only;
     if (d.dim < 1 || d.dim > 3)
       throw InvalidArgument("rj_offline_create: dim must be 1, 2 or 3");
     if (!(d.n_export <= d.n_owned && d.n_owned <= d.n_relevant))
@@ -71,14 +77,17 @@ namespace rjb
         !d.lumped_mass_matrix)
       throw InvalidArgument("rj_offline_create: null stencil arrays");
 
-    int n_dev = 0;
-    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
-      throw NoDevice("rj_offline_create: no CUDA device (there is no CPU fallback)");
-    RJ_CUDA(cudaSetDevice(device));
+    if (!host_only) {
+      int n_dev = 0;
+      if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        throw NoDevice("rj_offline_create: no CUDA device (there is no CPU fallback)");
+      RJ_CUDA(cudaSetDevice(device));
+    }
 
     auto *od = new rj_offline();
     try {
       od->device = device;
+      od->host_only = host_only;
       od->dim = d.dim;
       od->n_export = d.n_export;
       od->n_owned = d.n_owned;
@@ -217,8 +226,9 @@ namespace rjb
             buf[od->entry(i, c)] = d.mass_matrix[host_entry_index(d, i, c, 1, 0)];
         od->mij = upload(buf);
 
-        RJ_CUDA(cudaMalloc(&od->cij, size_t(dim) * E_owned * sizeof(double)));
-        for (int q = 0; q < dim; ++q) {
+        if (!host_only)
+          RJ_CUDA(cudaMalloc(&od->cij, size_t(dim) * E_owned * sizeof(double)));
+        for (int q = 0; q < dim && !host_only; ++q) {
           std::fill(buf.begin(), buf.end(), 0.);
 #pragma omp parallel for schedule(static)
           for (uint32_t i = 0; i < n_owned; ++i)
@@ -344,6 +354,8 @@ namespace rjb
         od->n_mat_send = uint32_t(mat_send.size());
         od->send_rows = upload(send_rows);
         od->mat_send_entries = upload(mat_send);
+        od->h_send_rows = send_rows;
+        od->h_mat_send_entries = mat_send;
       }
 
       if (d.positions) {
@@ -354,6 +366,10 @@ namespace rjb
         od->positions = upload(pos);
       }
 
+      if (host_only) {
+        od->h_cols.swap(cols);
+        od->h_transposed.swap(idxT);
+      }
     } catch (...) {
       delete od;
       throw;

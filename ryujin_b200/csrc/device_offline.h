@@ -69,7 +69,9 @@ struct rj_offline {
   /* host mirrors for introspection / CSR <-> sliced index maps */
   std::vector<uint32_t> h_slice_offsets;
   std::vector<uint32_t> h_row_length;
-  std::vector<uint32_t> h_cols, h_transposed; /* kept only if small */
+  std::vector<uint32_t> h_cols, h_transposed; /* host-only layouts */
+  std::vector<uint32_t> h_send_rows, h_mat_send_entries;
+  bool host_only = false;
 
   uint32_t entry(uint32_t row, uint32_t col) const
   {
@@ -81,5 +83,5 @@ struct rj_offline {
 
 namespace rjb
 {
-  rj_offline *build_device_offline(const rj_offline_desc &desc, int device);
+  rj_offline *build_device_offline(const rj_offline_desc &desc, int device, bool host_only = false);
 }

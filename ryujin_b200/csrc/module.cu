@@ -726,6 +726,55 @@ int rj_offline_create(rj_offline **out, const rj_offline_desc *desc, int device)
   });
 }
 
+int rj_offline_create_host_layout(rj_offline **out, const rj_offline_desc *desc)
+{
+  return guarded([&] {
+    if (!out || !desc)
+      throw InvalidArgument("rj_offline_create_host_layout: null argument");
+    *out = build_device_offline(*desc, 0, /*host_only=*/true);
+    return RJ_OK;
+  });
+}
+
+int rj_offline_exchange_sizes(const rj_offline *od, uint64_t sizes[3])
+{
+  return guarded([&] {
+    if (!od)
+      throw InvalidArgument("null offline data");
+    sizes[0] = od->neighbors.size();
+    sizes[1] = od->n_send_rows;
+    sizes[2] = od->n_mat_send;
+    return RJ_OK;
+  });
+}
+
+int rj_offline_exchange_get(const rj_offline *od, uint32_t *neighbor_info, uint32_t *send_rows, uint32_t *mat_send_entries)
+{
+  return guarded([&] {
+    if (!od)
+      throw InvalidArgument("null offline data");
+    if (neighbor_info)
+      for (size_t p = 0; p < od->neighbors.size(); ++p) {
+        const auto &nb = od->neighbors[p];
+        uint32_t *o = neighbor_info + 9 * p;
+        o[0] = uint32_t(nb.rank);
+        o[1] = nb.ghost_start;
+        o[2] = nb.ghost_count;
+        o[3] = nb.send_offset;
+        o[4] = nb.send_count;
+        o[5] = nb.mat_send_offset;
+        o[6] = nb.mat_send_count;
+        o[7] = nb.mat_recv_offset;
+        o[8] = nb.mat_recv_count;
+      }
+    if (send_rows)
+      std::memcpy(send_rows, od->h_send_rows.data(), od->h_send_rows.size() * sizeof(uint32_t));
+    if (mat_send_entries)
+      std::memcpy(mat_send_entries, od->h_mat_send_entries.data(), od->h_mat_send_entries.size() * sizeof(uint32_t));
+    return RJ_OK;
+  });
+}
+
 void rj_offline_destroy(rj_offline *od) { delete od; }
 
 int rj_offline_layout_sizes(const rj_offline *od, uint64_t sizes[4])
@@ -750,13 +799,21 @@ int rj_offline_layout_get(const rj_offline *od,
   return guarded([&] {
     if (!od)
       throw InvalidArgument("null offline data");
-    RJ_CUDA(cudaSetDevice(od->device));
+    if (!od->host_only)
+      RJ_CUDA(cudaSetDevice(od->device));
     if (slice_offsets)
       for (uint32_t g = 0; g <= od->n_slices; ++g)
         slice_offsets[g] = od->h_slice_offsets[g];
     if (row_length)
       for (uint32_t i = 0; i < od->n_owned; ++i)
         row_length[i] = od->h_row_length[i];
+    if (od->host_only) {
+      if (cols)
+        std::memcpy(cols, od->h_cols.data(), size_t(od->E_owned) * sizeof(uint32_t));
+      if (transposed)
+        std::memcpy(transposed, od->h_transposed.data(), size_t(od->E_owned) * sizeof(uint32_t));
+      return RJ_OK;
+    }
     if (cols)
       RJ_CUDA(cudaMemcpy(cols, od->cols, size_t(od->E_owned) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (transposed)
@@ -868,6 +925,8 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
       throw InvalidArgument("rj_hyperbolic_module_create: null argument");
     if (mp->limiter_iterations > 2)
       throw InvalidArgument("The number of limiter iterations must be between [0,2]");
+    if (od->host_only)
+      throw NoDevice("rj_hyperbolic_module_create: offline data is a host-only layout (no CPU fallback)");
     if (!od->neighbors.empty() && !comm)
       throw InvalidArgument("rj_hyperbolic_module_create: offline data has ghost rows but comm is NULL");
     RJ_CUDA(cudaSetDevice(od->device));

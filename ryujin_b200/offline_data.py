@@ -149,11 +149,15 @@ class OfflineData:
     """Device resident stencil data (rj_offline): sliced-ELL matrices, lumped
     mass, boundary map, coupling pairs and halo lists on one GPU."""
 
-    def __init__(self, host, device=0):
+    def __init__(self, host, device=0, host_layout_only=False):
         self.host = host
         self.device = device
+        self.host_layout_only = host_layout_only
         h = C.c_void_p()
-        check(lib.rj_offline_create(C.byref(h), C.byref(host.desc), device))
+        if host_layout_only:
+            check(lib.rj_offline_create_host_layout(C.byref(h), C.byref(host.desc)))
+        else:
+            check(lib.rj_offline_create(C.byref(h), C.byref(host.desc), device))
         self._h = h
         sizes = (C.c_uint64 * 4)()
         check(lib.rj_offline_layout_sizes(self._h, sizes))
@@ -190,6 +194,21 @@ class OfflineData:
         check(lib.rj_offline_layout_get(self._h, so.ctypes.data_as(_lib.u64p), rl.ctypes.data_as(_lib.u32p),
                                         cols.ctypes.data_as(_lib.u32p), tr.ctypes.data_as(_lib.u32p)))
         return so, rl, cols, tr
+
+    def exchange_lists(self):
+        """(neighbors, send_rows, mat_send_entries); neighbors: list of dicts"""
+        sizes = (C.c_uint64 * 3)()
+        check(lib.rj_offline_exchange_sizes(self._h, sizes))
+        nn, ns, nm = (int(x) for x in sizes)
+        info = np.zeros(9 * max(nn, 1), dtype=np.uint32)
+        rows = np.zeros(max(ns, 1), dtype=np.uint32)
+        ents = np.zeros(max(nm, 1), dtype=np.uint32)
+        check(lib.rj_offline_exchange_get(self._h, info.ctypes.data_as(_lib.u32p), rows.ctypes.data_as(_lib.u32p),
+                                          ents.ctypes.data_as(_lib.u32p)))
+        keys = ("rank", "ghost_start", "ghost_count", "send_offset", "send_count", "mat_send_offset",
+                "mat_send_count", "mat_recv_offset", "mat_recv_count")
+        neighbors = [dict(zip(keys, (int(v) for v in info[9 * p : 9 * p + 9]))) for p in range(nn)]
+        return neighbors, rows[:ns], ents[:nm]
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Multi-GPU parity (run on an N-GPU box):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multi_gpu_parity.py
+
+Every rank owns a z-slab (y-slab in 2D) of the same global mesh; ghost values travel over
+NCCL (C1-C9 of SURVEY.md 2b).  Rank 0 additionally runs the whole mesh on its own GPU and
+compares the gathered multi-rank state with it.  As in the reference (mpirun=4 vs mpirun=8
+goldens) the result depends on the partition at round-off level only: d_ij across a rank
+boundary is computed by each owner in its own operand order
+(hyperbolic_module.template.h:334-337).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import ryujin_b200 as rj  # noqa: E402
+from helpers import CASES, make_mesh, rel_linf  # noqa: E402
+
+
+def run(case, n_cells, cycles, rank, world, comm, device, **ti_kw):
+    c = CASES[case]
+    mesh = make_mesh(case, n_cells)
+    iv = dict(c["iv"])
+    kind = getattr(rj.InitialState, iv.pop("kind"))
+    od = rj.OfflineData.from_mesh(mesh, rank=rank, n_ranks=world, device=device)
+    module = rj.HyperbolicModule(od, rj.HyperbolicSystem(), rj.InitialValues(kind, **iv), comm=comm)
+    ti = rj.TimeIntegrator(module, rj.TimeSteppingScheme.erk_33, **ti_kw)
+    state = module.state_vector()
+    state.interpolate(0.0)
+    t, taus = 0.0, []
+    for _ in range(cycles):
+        tau = ti.step(state, t)
+        taus.append(tau)
+        t += tau
+    return od, module, state.download(), np.array(taus)
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = rj.Communicator.from_torch_distributed(local)
+    ok = True
+    for case, n_cells, cycles, kw, tol in (
+        ("vortex3d", [24, 24, 8 * world], 10, dict(cfl_min=0.2, cfl_max=0.2, cfl_recovery_strategy=rj.CFLRecoveryStrategy.none), 1e-12),
+        ("sod2d", [64, 16 * world], 20, dict(), 1e-7),
+        ("sod3d", [32, 8, 8 * world], 10, dict(), 1e-7),
+    ):
+        od, module, U, taus = run(case, n_cells, cycles, rank, world, comm, local, **kw)
+        n_global = od.host.n_global_dofs
+        k = module.k
+        # gather (global index, U) on rank 0
+        full = torch.zeros((n_global, k), dtype=torch.float64, device="cuda")
+        idx = torch.from_numpy(od.host.global_index[: od.host.n_owned].astype(np.int64)).cuda()
+        full[idx] = torch.from_numpy(U).cuda()
+        dist.all_reduce(full)  # disjoint ownership: sum == gather
+        counters = torch.tensor([module.n_restarts(), module.n_warnings()], device="cuda")
+        if rank == 0:
+            od1, module1, U1, taus1 = run(case, n_cells, cycles, 0, 1, None, local, **kw)
+            g1 = od1.host.global_index[: od1.host.n_owned].astype(np.int64)
+            ref = np.zeros((n_global, k))
+            ref[g1] = U1
+            err = rel_linf(full.cpu().numpy(), ref)
+            dtau = float(np.max(np.abs(taus - taus1) / taus1))
+            same = (module1.n_restarts(), module1.n_warnings()) == tuple(int(x) for x in counters.tolist())
+            print("multi-gpu %s %s x%d ranks, %d cycles: rel Linf vs single GPU %.3e, tau %.2e, counters equal %s"
+                  % (case, n_cells, world, cycles, err, dtau, same), flush=True)
+            ok = ok and err < tol and dtau < max(tol, 1e-12)
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    if not flag.item():
+        raise SystemExit(1)
+    if rank == 0:
+        print("multi-gpu parity ok")
+
+
+if __name__ == "__main__":
+    main()
