@@ -393,7 +393,30 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1: keep the contract of ONE
+    JSON line on stdout by routing fd 1 to stderr and returning a handle on the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    # torchrun exports OMP_NUM_THREADS=1; the host-side mesh generator and the CPU baseline are
+    # OpenMP parallel: give every rank its share of the cores before the libraries load
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if os.environ.get("OMP_NUM_THREADS", "1") == "1" or world > 1:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(world, 1)))
+    real_stdout = _quiet_stdout()
+    import builtins
+
+    def emit(*a, **k):
+        k.setdefault("file", real_stdout)
+        builtins.print(*a, **k)
+        real_stdout.flush()
+
+    globals()["print"] = emit
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
