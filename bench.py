@@ -42,7 +42,10 @@ def algorithmic_bytes(dim, s=None):
     s = s if s is not None else 3**dim
     per_pass = {
         "precompute": w * (k + p),
-        "dij_alpha": s * (d * w + 4 + w) + w * (k + p + 2),
+        # step 2 of the reference is one pass (1044 B in 3D); here it is two kernels, the split
+        # re-reads cols and c_ij once more -- that extra traffic is NOT counted as algorithmic
+        "dij": s * (d * w + 4 + w) + w * k,
+        "alpha": w * (p + 2),
         "dii_tau": s * (2 * w + 4) + w,
         "low_order": s * (w * (d + 2 + k) + 4) + w * (3 * k + p + b + 3),
         "pij_lij": s * (2 * k * w + 2 * w + 4) + w * (b + 2 * k + 1),
@@ -313,7 +316,8 @@ def run_ours(args):
     peak, peak_kind = measured_peak_gbs()
     kernel_ms = {name: v for name, v in prof.items() if v[1] > 0}
     total_prof_ms = sum(v[0] for v in kernel_ms.values())
-    dominant = max((n for n in kernel_ms if n in per_pass), key=lambda n: kernel_ms[n][0])
+    candidates = [n for n in kernel_ms if n in per_pass and n != "alpha"]
+    dominant = max(candidates, key=lambda n: kernel_ms[n][0])
     dom_ms, dom_count = kernel_ms[dominant]
     # low_order reads one extra state vector per ERK stage: (0 + 1 + 2)/3 = 1 on average
     extra = 8 * k * 1.0 if dominant == "low_order" else 0.0

@@ -366,10 +366,10 @@ uint64_t rj_hyperbolic_module_kernel_launches(const rj_hyperbolic_module *hm);
 
 /* Per-kernel device time, measured with CUDA events on the module's stream
  * around every launch while profiling is on (bench.py roofline).  Slots:
- * 0 boundary conditions, 1 precompute, 2 d_ij + alpha, 3 boundary d_ij,
- * 4 d_ii + tau, 5 low-order update, 6 P_ij + l_ij, 7 high-order + next l_ij,
- * 8 final high-order update, 9 plumbing (pack, scalars). */
-#define RJ_N_PROFILE_SLOTS 10
+ * 0 boundary conditions, 1 precompute, 2 d_ij (edge parallel), 3 alpha,
+ * 4 boundary d_ij, 5 d_ii + tau, 6 low-order update, 7 P_ij + l_ij,
+ * 8 high-order + next l_ij, 9 final high-order update, 10 plumbing. */
+#define RJ_N_PROFILE_SLOTS 11
 int rj_hyperbolic_module_set_profiling(rj_hyperbolic_module *hm, int on);
 int rj_hyperbolic_module_get_profile(rj_hyperbolic_module *hm, double ms[RJ_N_PROFILE_SLOTS], uint64_t counts[RJ_N_PROFILE_SLOTS]);
 

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libryujin_b200.so")
+# RYUJIN_B200_LIB selects an alternative build of the same library (tuning experiments)
+LIB_PATH = os.environ.get("RYUJIN_B200_LIB") or os.path.join(_HERE, "libryujin_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -16,7 +17,34 @@ if not os.path.exists(LIB_PATH):
         "or `make -C ryujin_b200/csrc`. There is no CPU fallback." % LIB_PATH
     )
 
-lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+
+
+def _preload_nccl():
+    """libryujin_b200.so links libnccl.so.2 by soname.  PyTorch bundles a newer NCCL than the
+    system one; whichever copy is mapped first serves both, so map PyTorch's copy first (if it
+    exists) -- otherwise a later `import torch` fails on symbols missing from the older build."""
+    import importlib.util
+
+    for name in ("nvidia.nccl", "nvidia"):
+        try:
+            spec = importlib.util.find_spec(name)
+        except (ImportError, ValueError):
+            spec = None
+        if spec is None or not spec.submodule_search_locations:
+            continue
+        for base in spec.submodule_search_locations:
+            for cand in (os.path.join(base, "lib", "libnccl.so.2"), os.path.join(base, "nccl", "lib", "libnccl.so.2")):
+                if os.path.exists(cand):
+                    try:
+                        C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                        return cand
+                    except OSError:
+                        pass
+    return None
+
+
+NCCL_PATH = _preload_nccl()
+lib = C.CDLL(LIB_PATH)
 
 RJ_OK, RJ_RESTART = 0, 1
 RJ_ERR_INVALID, RJ_ERR_CUDA, RJ_ERR_NCCL, RJ_ERR_NUMERIC, RJ_ERR_NO_DEVICE = -1, -2, -3, -4, -5

@@ -78,6 +78,13 @@ namespace rjb
       prec[1] = harten_entropy(p, U);
     }
 
+    /* Per-node part of flux_contribution (1/rho, p), stored once per prepared
+     * state vector next to the precomputed values instead of being recomputed
+     * for every stencil entry (the reference recomputes f(U_j) per entry,
+     * indicator.h:228, hyperbolic_module.template.h:760-761).  Same operations,
+     * same rounding: values are bit-identical to flux_contribution(). */
+    static constexpr int n_aux = 2;
+
     RJ_DEVICE static void
     harten_entropy_derivative(const Params &p, const double (&U)[k], double (&result)[k])
     {
@@ -101,6 +108,21 @@ namespace rjb
     struct Flux {
       double rho_inverse, p;
     };
+
+    RJ_DEVICE static void store_aux(const Flux &f, double (&aux)[n_aux])
+    {
+      aux[0] = f.rho_inverse;
+      aux[1] = f.p;
+    }
+
+    RJ_DEVICE static Flux load_aux(const double (&aux)[n_aux])
+    {
+      Flux f;
+      f.rho_inverse = aux[0];
+      f.p = aux[1];
+      return f;
+    }
+
 
     RJ_DEVICE static Flux
     flux_contribution(const Params &prm, const double (&/*prec*/)[n_prec], const double (&U)[k])
@@ -454,10 +476,10 @@ namespace rjb
                                 const double (&/*prec_i*/)[n_prec],
                                 const double (&U_j)[k],
                                 const double (&prec_j)[n_prec],
+                                const Flux &fj,
                                 const double (&c_ij)[dim])
       {
         const double eta_j = prec_j[1];
-        Flux fj = flux_contribution(p, prec_j, U_j);
         Flux fi;
         fi.rho_inverse = rho_i_inverse;
         fi.p = p_i;

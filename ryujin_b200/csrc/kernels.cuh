@@ -15,6 +15,24 @@
 
 #include "device_common.cuh"
 
+/* minimum resident blocks of 128 threads per SM requested from ptxas for the four
+ * FP64-heavy kernels (caps registers at 65536 / (128 * MB)); tuned in profiles/ */
+#ifndef RJ_MB_DIJ
+#define RJ_MB_DIJ 3 /* blocks of 256 threads */
+#endif
+#ifndef RJ_MB_ALPHA
+#define RJ_MB_ALPHA 6
+#endif
+#ifndef RJ_MB_LOW
+#define RJ_MB_LOW 4
+#endif
+#ifndef RJ_MB_PIJ
+#define RJ_MB_PIJ 5
+#endif
+#ifndef RJ_MB_HO
+#define RJ_MB_HO 8
+#endif
+
 namespace rjb
 {
   struct StencilView {
@@ -43,6 +61,7 @@ namespace rjb
   struct StagePointers {
     const double *U[n > 0 ? n : 1];
     const double *prec[n > 0 ? n : 1];
+    const double *aux[n > 0 ? n : 1];
     double weight[n > 0 ? n : 1];
   };
 
@@ -153,64 +172,82 @@ namespace rjb
   template <class Eq>
   __global__ void k_precompute(StencilView v,
                                typename Eq::Params prm,
-                               uint32_t row_begin,
-                               uint32_t row_end,
+                               uint32_t n_relevant,
                                const double *__restrict__ U,
-                               double *__restrict__ prec)
+                               double *__restrict__ prec,
+                               double *__restrict__ aux)
   {
-    constexpr int k = Eq::k, np = Eq::n_prec;
-    RowInfo r;
-    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+    /* owned rows as in the reference; ghost rows are recomputed locally from the
+     * exchanged ghost state (bit-identical to the owner's values), which replaces
+     * the ghost exchange of the precomputed vector (C2, :157-160) */
+    constexpr int k = Eq::k, np = Eq::n_prec, na = Eq::n_aux;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_relevant)
       return;
-    double U_i[k], prec_i[np];
-    load_state<k>(U, v.ld, r.i, U_i);
+    if (i < v.n_owned && v.row_length[i] <= 1)
+      return;
+    double U_i[k], prec_i[np], aux_i[na];
+    load_state<k>(U, v.ld, i, U_i);
     Eq::precompute(prm, U_i, prec_i);
-    store_state<np>(prec, v.ld, r.i, prec_i);
+    Eq::store_aux(Eq::flux_contribution(prm, prec_i, U_i), aux_i);
+    store_state<np>(prec, v.ld, i, prec_i);
+    store_state<na>(aux, v.ld, i, aux_i);
   }
 
 
   /* ---------------------------------------------------------------------- *
    * Step 2: off-diagonal d_ij for j > i and alpha_i,
-   * hyperbolic_module.template.h:341-424.  Additionally mirrors d_ij into the
-   * transposed slot (j, i), which replaces the gather of step 3 (:511-535).
+   * hyperbolic_module.template.h:341-424, as two kernels:
+   *
+   *  k_dij   EDGE parallel: block = one slice of 32 rows x W warps; warp w takes
+   *          columns w, w+W, ... of the slice, so one thread runs one or two
+   *          Riemann solves instead of ~13 in sequence.  The per-edge solve is a
+   *          long dependent FP64 chain (2 pow, 7 sqrt, 9 div); spreading it over
+   *          8x more, lighter threads is what fills the FP64 pipe (profiles/).
+   *          Also mirrors d_ij into the transposed slot (j, i), which replaces
+   *          the gather of step 3 (:511-535).
+   *  k_alpha ROW parallel: the entropy-viscosity commutator, accumulated in
+   *          column order in one thread as the reference does.
    * ---------------------------------------------------------------------- */
-  template <class Eq>
-  __global__ void __launch_bounds__(128) k_dij_alpha(StencilView v,
-                                                     typename Eq::Params prm,
-                                                     uint32_t row_begin,
-                                                     uint32_t row_end,
-                                                     const double *__restrict__ U,
-                                                     const double *__restrict__ prec,
-                                                     double *__restrict__ dij,
-                                                     double *__restrict__ alpha)
+  template <class Eq, int W>
+  __global__ void __launch_bounds__(32 * W, RJ_MB_DIJ) k_dij(StencilView v,
+                                                             typename Eq::Params prm,
+                                                             uint32_t slice_begin,
+                                                             uint32_t slice_end,
+                                                             const double *__restrict__ U,
+                                                             const double *__restrict__ prec,
+                                                             double *__restrict__ dij)
   {
     constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec;
-    RowInfo r;
-    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+    const uint32_t g = slice_begin + blockIdx.x;
+    if (g >= slice_end)
       return;
-    const uint32_t i = r.i;
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t i = (g << 5) + lane;
+    if (i >= v.n_owned)
+      return;
+    const uint32_t len = v.row_length[i];
+    if (len <= 1)
+      return;
+    const uint32_t base = v.slice_offsets[g] + lane;
 
     double U_i[k], prec_i[np];
     load_state<k>(U, v.ld, i, U_i);
     load_state<np>(prec, v.ld, i, prec_i);
 
-    typename Eq::Indicator indicator;
-    indicator.reset(prm, prec_i, U_i);
-
-    for (uint32_t col = 0; col < r.len; ++col) {
-      const uint32_t e = r.base + col * 32;
+    for (uint32_t col = w; col < len; col += W) {
+      if (col == 0)
+        continue;
+      const uint32_t e = base + col * 32;
       const uint32_t j = v.cols[e];
+      if (j < i)
+        continue;
       double U_j[k], prec_j[np], c_ij[dim];
       load_state<k>(U, v.ld, j, U_j);
       load_state<np>(prec, v.ld, j, prec_j);
 #pragma unroll
       for (int d = 0; d < dim; ++d)
         c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
-
-      indicator.accumulate(prm, U_i, prec_i, U_j, prec_j, c_ij);
-
-      if (col == 0 || j < i)
-        continue;
 
       double nrm2 = c_ij[0] * c_ij[0];
 #pragma unroll
@@ -228,6 +265,43 @@ namespace rjb
       const uint32_t eT = v.transposed[e];
       if (eT < v.E_owned)
         dij[eT] = d_ij;
+    }
+  }
+
+  template <class Eq>
+  __global__ void __launch_bounds__(128, RJ_MB_ALPHA) k_alpha(StencilView v,
+                                                              typename Eq::Params prm,
+                                                              uint32_t row_begin,
+                                                              uint32_t row_end,
+                                                              const double *__restrict__ U,
+                                                              const double *__restrict__ prec,
+                                                              const double *__restrict__ aux,
+                                                              double *__restrict__ alpha)
+  {
+    constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec, na = Eq::n_aux;
+    RowInfo r;
+    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+      return;
+    const uint32_t i = r.i;
+
+    double U_i[k], prec_i[np];
+    load_state<k>(U, v.ld, i, U_i);
+    load_state<np>(prec, v.ld, i, prec_i);
+
+    typename Eq::Indicator indicator;
+    indicator.reset(prm, prec_i, U_i);
+
+    for (uint32_t col = 0; col < r.len; ++col) {
+      const uint32_t e = r.base + col * 32;
+      const uint32_t j = v.cols[e];
+      double U_j[k], prec_j[np], aux_j[na], c_ij[dim];
+      load_state<k>(U, v.ld, j, U_j);
+      load_state<np>(prec, v.ld, j, prec_j);
+      load_state<na>(aux, v.ld, j, aux_j);
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
+      indicator.accumulate(prm, U_i, prec_i, U_j, prec_j, Eq::load_aux(aux_j), c_ij);
     }
 
     const double hd_i = v.mi[i] * v.measure_of_omega_inverse;
@@ -362,12 +436,13 @@ namespace rjb
    * hyperbolic_module.template.h:597-884.
    * ---------------------------------------------------------------------- */
   template <class Eq, int stages>
-  __global__ void __launch_bounds__(128) k_low_order(StencilView v,
+  __global__ void __launch_bounds__(128, RJ_MB_LOW) k_low_order(StencilView v,
                                                      typename Eq::Params prm,
                                                      uint32_t row_begin,
                                                      uint32_t row_end,
                                                      const double *__restrict__ U,
                                                      const double *__restrict__ prec,
+                                                     const double *__restrict__ aux,
                                                      StagePointers<stages> st,
                                                      const double *__restrict__ alpha,
                                                      const double *__restrict__ dij,
@@ -377,7 +452,7 @@ namespace rjb
                                                      double *__restrict__ bounds,
                                                      double *__restrict__ pij)
   {
-    constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec, nb = Eq::n_bounds;
+    constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec, nb = Eq::n_bounds, na = Eq::n_aux;
     RowInfo r;
     if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
       return;
@@ -397,16 +472,18 @@ namespace rjb
     const double m_i = v.mi[i];
     const double m_i_inv = v.mi_inv[i];
 
-    const typename Eq::Flux flux_i = Eq::flux_contribution(prm, prec_i, U_i);
+    double aux_i[na];
+    load_state<na>(aux, v.ld, i, aux_i);
+    const typename Eq::Flux flux_i = Eq::load_aux(aux_i);
 
     double U_is[stages > 0 ? stages : 1][k];
     typename Eq::Flux flux_is[stages > 0 ? stages : 1];
 #pragma unroll
     for (int s = 0; s < stages; ++s) {
-      double prec_s[np];
+      double aux_s[na];
       load_state<k>(st.U[s], v.ld, i, U_is[s]);
-      load_state<np>(st.prec[s], v.ld, i, prec_s);
-      flux_is[s] = Eq::flux_contribution(prm, prec_s, U_is[s]);
+      load_state<na>(st.aux[s], v.ld, i, aux_s);
+      flux_is[s] = Eq::load_aux(aux_s);
     }
 
     double U_i_new[k], F_iH[k];
@@ -443,7 +520,9 @@ namespace rjb
       for (int d = 0; d < dim; ++d)
         scaled_c_ij[d] = c_ij[d] * scale;
 
-      const typename Eq::Flux flux_j = Eq::flux_contribution(prm, prec_j, U_j);
+      double aux_j[na];
+      load_state<na>(aux, v.ld, j, aux_j);
+      const typename Eq::Flux flux_j = Eq::load_aux(aux_j);
 
       double flux_ij[k], P_ij[k];
       Eq::flux_divergence(U_i, flux_i, U_j, flux_j, c_ij, flux_ij);
@@ -471,10 +550,10 @@ namespace rjb
 
 #pragma unroll
       for (int s = 0; s < stages; ++s) {
-        double U_js[k], prec_js[np], flux_ij_s[k];
+        double U_js[k], aux_js[na], flux_ij_s[k];
         load_state<k>(st.U[s], v.ld, j, U_js);
-        load_state<np>(st.prec[s], v.ld, j, prec_js);
-        const typename Eq::Flux flux_js = Eq::flux_contribution(prm, prec_js, U_js);
+        load_state<na>(st.aux[s], v.ld, j, aux_js);
+        const typename Eq::Flux flux_js = Eq::load_aux(aux_js);
         Eq::flux_divergence(U_is[s], flux_is[s], U_js, flux_js, c_ij, flux_ij_s);
 #pragma unroll
         for (int q = 0; q < k; ++q) {
@@ -503,7 +582,7 @@ namespace rjb
    * hyperbolic_module.template.h:892-1041.
    * ---------------------------------------------------------------------- */
   template <class Eq>
-  __global__ void __launch_bounds__(128) k_pij_lij(StencilView v,
+  __global__ void __launch_bounds__(128, RJ_MB_PIJ) k_pij_lij(StencilView v,
                                                    typename Eq::Params prm,
                                                    uint32_t row_begin,
                                                    uint32_t row_end,
@@ -567,7 +646,7 @@ namespace rjb
    * hyperbolic_module.template.h:1053-1182.
    * ---------------------------------------------------------------------- */
   template <class Eq, bool last_round>
-  __global__ void __launch_bounds__(128) k_high_order(StencilView v,
+  __global__ void __launch_bounds__(128, RJ_MB_HO) k_high_order(StencilView v,
                                                       typename Eq::Params prm,
                                                       uint32_t row_begin,
                                                       uint32_t row_end,

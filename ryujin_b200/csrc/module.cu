@@ -69,6 +69,7 @@ struct rj_state {
   int device = 0; /* destruction must not depend on the module still being alive */
   double *U = nullptr;    /* k * ld */
   double *prec = nullptr; /* n_prec * ld */
+  double *aux = nullptr;  /* n_aux * ld: per-node part of the flux contribution (1/rho, p) */
 };
 
 /* ------------------------------------------------------------------------ */
@@ -89,7 +90,7 @@ struct rj_hyperbolic_module {
   uint32_t n_restarts = 0, n_warnings = 0;
   uint64_t launches = 0;
 
-  int k = 0, n_prec = 0, n_bounds = 0;
+  int k = 0, n_prec = 0, n_bounds = 0, n_aux = 0;
 
   /* scratch, hyperbolic_module.h:319-333 */
   double *alpha = nullptr, *bounds = nullptr, *r = nullptr;
@@ -187,6 +188,7 @@ struct rj_hyperbolic_module {
     P_BC = 0,
     P_PRECOMPUTE,
     P_DIJ_ALPHA,
+    P_ALPHA,
     P_BOUNDARY_DIJ,
     P_DII_TAU,
     P_LOW_ORDER,
@@ -380,6 +382,7 @@ namespace rjb
       k = Eq::k;
       n_prec = Eq::n_prec;
       n_bounds = Eq::n_bounds;
+      n_aux = Eq::n_aux;
     }
 
     /* rows [begin, end), begin multiple of 32 */
@@ -428,10 +431,9 @@ namespace rjb
              state.U);
       tag(P_OTHER);
       exchange_vector(state.U, Eq::k); /* C1 */
+      /* precomputed values for owned AND ghost rows from the exchanged state: replaces C2 */
       tag(P_PRECOMPUTE);
-      launch_rows(k_precompute<Eq>, 0, od->n_owned, v, prm, 0u, od->n_owned, state.U, state.prec);
-      tag(P_OTHER);
-      exchange_vector(state.prec, Eq::n_prec); /* C2 */
+      launch(k_precompute<Eq>, od->n_relevant, 256, v, prm, od->n_relevant, state.U, state.prec, state.aux);
     }
 
     template <int stages>
@@ -444,6 +446,7 @@ namespace rjb
       for (int s = 0; s < stages; ++s) {
         st.U[s] = stage_states[s]->U;
         st.prec[s] = stage_states[s]->prec;
+        st.aux[s] = stage_states[s]->aux;
         st.weight[s] = stage_weights[s];
       }
       launch_rows(k_low_order<Eq, stages>,
@@ -455,6 +458,7 @@ namespace rjb
                   od->n_owned,
                   old_state.U,
                   old_state.prec,
+                  old_state.aux,
                   st,
                   alpha,
                   dij,
@@ -488,7 +492,16 @@ namespace rjb
 
       /* Step 2: d_ij (j > i), alpha_i; then C3 */
       tag(P_DIJ_ALPHA);
-      launch_rows(k_dij_alpha<Eq>, 0, n_owned, v, prm, 0u, n_owned, old_state.U, old_state.prec, dij, alpha);
+      {
+        constexpr int W = 8; /* warps per slice in the edge-parallel d_ij kernel */
+        if (od->n_slices > 0) {
+          k_dij<Eq, W><<<od->n_slices, 32 * W, 0, stream>>>(v, prm, 0u, od->n_slices, old_state.U, old_state.prec, dij);
+          RJ_CUDA(cudaGetLastError());
+          ++launches;
+        }
+      }
+      tag(P_ALPHA);
+      launch_rows(k_alpha<Eq>, 0, n_owned, v, prm, 0u, n_owned, old_state.U, old_state.prec, old_state.aux, alpha);
       tag(P_OTHER);
       exchange_vector(alpha, 1);
 
@@ -1173,6 +1186,8 @@ int rj_state_create(rj_state **out, rj_hyperbolic_module *hm)
     const size_t ld = hm->od->ld;
     RJ_CUDA(cudaMalloc(&s->U, size_t(hm->k) * ld * sizeof(double)));
     RJ_CUDA(cudaMalloc(&s->prec, size_t(hm->n_prec) * ld * sizeof(double)));
+    RJ_CUDA(cudaMalloc(&s->aux, size_t(hm->n_aux) * ld * sizeof(double)));
+    RJ_CUDA(cudaMemsetAsync(s->aux, 0, size_t(hm->n_aux) * ld * sizeof(double), hm->stream));
     RJ_CUDA(cudaMemsetAsync(s->U, 0, size_t(hm->k) * ld * sizeof(double), hm->stream));
     RJ_CUDA(cudaMemsetAsync(s->prec, 0, size_t(hm->n_prec) * ld * sizeof(double), hm->stream));
     RJ_CUDA(cudaStreamSynchronize(hm->stream));
@@ -1188,6 +1203,7 @@ void rj_state_destroy(rj_state *s)
   cudaSetDevice(s->device);
   cudaFree(s->U);
   cudaFree(s->prec);
+  cudaFree(s->aux);
   delete s;
 }
 
@@ -1273,6 +1289,7 @@ int rj_state_swap(rj_state *a, rj_state *b)
       throw InvalidArgument("rj_state_swap: states of different modules");
     std::swap(a->U, b->U);
     std::swap(a->prec, b->prec);
+    std::swap(a->aux, b->aux);
     return RJ_OK;
   });
 }

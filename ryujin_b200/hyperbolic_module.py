@@ -281,7 +281,7 @@ class HyperbolicModule:
     def kernel_launches(self):
         return int(lib.rj_hyperbolic_module_kernel_launches(self._h))
 
-    PROFILE_SLOTS = ("boundary_conditions", "precompute", "dij_alpha", "boundary_dij", "dii_tau", "low_order",
+    PROFILE_SLOTS = ("boundary_conditions", "precompute", "dij", "alpha", "boundary_dij", "dii_tau", "low_order",
                      "pij_lij", "high_order_next_lij", "high_order_final", "plumbing")
 
     def set_profiling(self, on):
