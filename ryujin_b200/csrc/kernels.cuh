@@ -18,7 +18,32 @@
 /* minimum resident blocks of 128 threads per SM requested from ptxas for the four
  * FP64-heavy kernels (caps registers at 65536 / (128 * MB)); tuned in profiles/ */
 #ifndef RJ_MB_DIJ
-#define RJ_MB_DIJ 3 /* blocks of 256 threads */
+#define RJ_MB_DIJ 8 /* blocks of 32 * RJ_DIJ_W threads: 64 registers */
+#endif
+#define RJ_PRAGMA_(x) _Pragma(#x)
+#define RJ_PRAGMA(x) RJ_PRAGMA_(x)
+#define RJ_UNROLL(n) RJ_PRAGMA(unroll n)
+/* unroll factors of the column loops (software pipelining of the index -> gather chain) */
+#ifndef RJ_UNROLL_ALPHA
+#define RJ_UNROLL_ALPHA 1
+#endif
+#ifndef RJ_UNROLL_DII
+#define RJ_UNROLL_DII 4
+#endif
+#ifndef RJ_UNROLL_LOW
+#define RJ_UNROLL_LOW 3
+#endif
+#ifndef RJ_UNROLL_PIJ
+#define RJ_UNROLL_PIJ 1
+#endif
+#ifndef RJ_UNROLL_HO1
+#define RJ_UNROLL_HO1 4
+#endif
+#ifndef RJ_UNROLL_HO2
+#define RJ_UNROLL_HO2 3
+#endif
+#ifndef RJ_DIJ_W
+#define RJ_DIJ_W 4 /* warps per slice of the edge-parallel d_ij kernel */
 #endif
 #ifndef RJ_MB_ALPHA
 #define RJ_MB_ALPHA 6
@@ -291,6 +316,7 @@ namespace rjb
     typename Eq::Indicator indicator;
     indicator.reset(prm, prec_i, U_i);
 
+    RJ_UNROLL(RJ_UNROLL_ALPHA)
     for (uint32_t col = 0; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
       const uint32_t j = v.cols[e];
@@ -372,6 +398,7 @@ namespace rjb
     double tau_i = DBL_MAX;
     if (row_info(v, row_begin, row_end, r) && r.len > 1) {
       double d_sum = 0.;
+    RJ_UNROLL(RJ_UNROLL_DII)
       for (uint32_t col = 1; col < r.len; ++col)
         d_sum -= dij[r.base + col * 32];
       d_sum = fmin(d_sum, -1.e6 * DBL_MIN);
@@ -498,6 +525,7 @@ namespace rjb
 
     const double tau_m_i_inv = tau * m_i_inv;
 
+    RJ_UNROLL(RJ_UNROLL_LOW)
     for (uint32_t col = 0; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
       const uint32_t j = v.cols[e];
@@ -610,6 +638,7 @@ namespace rjb
     const double factor = tau * m_i_inv * lambda_inv;
 
     bool all_ok = true;
+    RJ_UNROLL(RJ_UNROLL_PIJ)
     for (uint32_t col = 1; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
       const uint32_t j = v.cols[e];
@@ -666,6 +695,7 @@ namespace rjb
     load_state<k>(U_new, v.ld, i, U_i_new);
     const double lambda = 1. / double(r.len - 1);
 
+    RJ_UNROLL(RJ_UNROLL_HO1)
     for (uint32_t col = 1; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
       const double l_ij = fmin(lij[e], lij[v.transposed[e]]);
@@ -681,6 +711,7 @@ namespace rjb
 
     double b[nb];
     load_state<nb>(bounds, v.ld, i, b);
+    RJ_UNROLL(RJ_UNROLL_HO2)
     for (uint32_t col = 1; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
       const double old_l_ij = fmin(lij[e], lij[v.transposed[e]]);

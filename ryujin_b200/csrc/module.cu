@@ -493,12 +493,8 @@ namespace rjb
       /* Step 2: d_ij (j > i), alpha_i; then C3 */
       tag(P_DIJ_ALPHA);
       {
-        constexpr int W = 8; /* warps per slice in the edge-parallel d_ij kernel */
-        if (od->n_slices > 0) {
-          k_dij<Eq, W><<<od->n_slices, 32 * W, 0, stream>>>(v, prm, 0u, od->n_slices, old_state.U, old_state.prec, dij);
-          RJ_CUDA(cudaGetLastError());
-          ++launches;
-        }
+        constexpr int W = RJ_DIJ_W; /* warps per slice in the edge-parallel d_ij kernel */
+        launch(k_dij<Eq, W>, size_t(od->n_slices) * 32 * W, 32 * W, v, prm, 0u, od->n_slices, old_state.U, old_state.prec, dij);
       }
       tag(P_ALPHA);
       launch_rows(k_alpha<Eq>, 0, n_owned, v, prm, 0u, n_owned, old_state.U, old_state.prec, old_state.aux, alpha);
