@@ -70,9 +70,31 @@ namespace
     return prm;
   }
 
+  sw::Parameters make_sw_params(const double *p)
+  {
+    /* layout documented in oracle/orc.py: SW_PARAM_FIELDS */
+    sw::Parameters prm;
+    prm.gravity = p[0];
+    prm.manning_friction_coefficient = p[1];
+    prm.reference_water_depth = p[2];
+    prm.dry_state_relaxation_factor = p[3];
+    prm.dry_state_relaxation_small = p[4];
+    prm.dry_state_relaxation_large = p[5];
+    prm.indicator_evc_factor = p[6];
+    prm.limiter_iterations = (unsigned int)p[7];
+    prm.limiter_newton_tolerance = p[8];
+    prm.limiter_newton_max_iterations = (unsigned int)p[9];
+    prm.limiter_relaxation_factor = p[10];
+    prm.limit_on_kinetic_energy = p[11] != 0.;
+    prm.limit_on_square_velocity = p[12] != 0.;
+    prm.expensive_bounds_check = p[13] != 0.;
+    return prm;
+  }
+
   struct SimBase {
     virtual ~SimBase() = default;
     virtual int k() const = 0;
+    virtual int n_bounds() const = 0;
     virtual unsigned int n() const = 0;
     virtual std::size_t nnz() const = 0;
     virtual void interpolate(double t, int slot) = 0;
@@ -95,6 +117,7 @@ namespace
     virtual void counters(unsigned int *restarts, unsigned int *warnings) const = 0;
     virtual double last_tau_max() const = 0;
     virtual void errors(double t, double *out3) = 0;
+    unsigned int error_mask = ~0u; /* bit c: include component c in the error norms */
   };
 
   template <int dim>
@@ -136,6 +159,7 @@ namespace
     }
 
     int k() const override { return Sys::k; }
+    int n_bounds() const override { return Sys::n_bounds; }
     unsigned int n() const override { return off->od.n_owned; }
     std::size_t nnz() const override { return off->od.cols.size(); }
 
@@ -243,6 +267,174 @@ namespace
       double linf = 0., l1 = 0., l2 = 0.;
       std::vector<double> a(n), e(n);
       for (int c = 0; c < Sys::k; ++c) {
+        if (!((error_mask >> c) & 1u))
+          continue;
+        for (unsigned int i = 0; i < n; ++i) {
+          a[i] = analytic[std::size_t(i) * Sys::k + c];
+          e[i] = slots[0].U[std::size_t(i) * Sys::k + c] - a[i];
+        }
+        const auto na = q1_norms<dim>(off->mesh, a);
+        const auto ne = q1_norms<dim>(off->mesh, e);
+        linf += ne[0] / na[0];
+        l1 += ne[1] / na[1];
+        l2 += ne[2] / na[2];
+      }
+      out3[0] = linf;
+      out3[1] = l1;
+      out3[2] = l2;
+    }
+  };
+  template <int dim>
+  struct SwSim : SimBase {
+    using Sys = sw::System<dim>;
+    using Desc = Description<Sys,
+                             sw::RiemannSolver<dim>,
+                             sw::Indicator<dim>,
+                             sw::Limiter<dim>>;
+    using Module = HyperbolicModule<Desc, dim>;
+    using SV = typename Module::StateVector;
+
+    OfflineHolder<dim> *off;
+    Sys sys;
+    sw::InitialValues<dim> iv;
+    std::unique_ptr<Module> module;
+    std::unique_ptr<TimeIntegrator<Desc, dim>> ti;
+    std::vector<SV> slots; /* slot 0 = the state vector of the time loop */
+
+    SwSim(OfflineHolder<dim> *o, const sw::Parameters &prm)
+        : off(o)
+        , sys(prm)
+        , iv(sys)
+    {
+    }
+
+    void finalize()
+    {
+      iv.transform.normalize();
+      module.reset(new Module(
+          off->od,
+          sys,
+          [this](const Vec<dim> &x, double t) { return iv.initial_state(x, t); },
+          std::vector<double>(off->od.n_owned, 0.) /* flat bathymetry */));
+      module->prepare();
+      ti.reset(new TimeIntegrator<Desc, dim>(*module));
+      ti->prepare();
+      slots.resize(6);
+      for (auto &s : slots)
+        s.reinit(off->od.n_owned);
+    }
+
+    int k() const override { return Sys::k; }
+    int n_bounds() const override { return Sys::n_bounds; }
+    unsigned int n() const override { return off->od.n_owned; }
+    std::size_t nnz() const override { return off->od.cols.size(); }
+
+    void positions_required() const
+    {
+      if (!off->has_mesh)
+        throw std::runtime_error("oracle: offline data has no mesh positions");
+    }
+
+    void interpolate(double t, int slot) override
+    {
+      positions_required();
+      auto &U = slots[slot].U;
+      for (unsigned int i = 0; i < off->od.n_owned; ++i) {
+        const auto s = iv.initial_state(off->mesh.position(i), t);
+        for (int c = 0; c < Sys::k; ++c)
+          U[std::size_t(i) * Sys::k + c] = s[c];
+      }
+    }
+
+    void set_U(int slot, const double *U) override
+    {
+      std::memcpy(slots[slot].U.data(), U, slots[slot].U.size() * sizeof(double));
+    }
+    void get_U(int slot, double *U) const override
+    {
+      std::memcpy(U, slots[slot].U.data(), slots[slot].U.size() * sizeof(double));
+    }
+    void get_prec(int slot, double *p) const override
+    {
+      std::memcpy(p, slots[slot].prec.data(), slots[slot].prec.size() * sizeof(double));
+    }
+    void prepare_state(int slot, double t) override
+    {
+      module->prepare_state_vector(slots[slot], t);
+    }
+    double hyp_step(int old_slot,
+                    int stages,
+                    const int *stage_slots,
+                    const double *weights,
+                    int new_slot,
+                    double tau,
+                    double tau_max) override
+    {
+      std::vector<const SV *> st;
+      std::vector<double> w;
+      for (int s = 0; s < stages; ++s) {
+        st.push_back(&slots[stage_slots[s]]);
+        w.push_back(weights[s]);
+      }
+      return module->step(slots[old_slot], st, w, slots[new_slot], tau, tau_max);
+    }
+    double ti_step(double t, double t_final) override
+    {
+      return ti->step(slots[0], t, t_final);
+    }
+    void set_cfl(double cfl) override { module->cfl(cfl); }
+    void set_strategy(int raise) override
+    {
+      module->id_violation_strategy_ = raise ? IDViolationStrategy::raise_exception
+                                             : IDViolationStrategy::warn;
+    }
+    void configure_ti(int scheme, double cfl_min, double cfl_max, int recovery) override
+    {
+      ti->time_stepping_scheme_ = TimeSteppingScheme(scheme);
+      ti->cfl_min_ = cfl_min;
+      ti->cfl_max_ = cfl_max;
+      ti->cfl_recovery_strategy_ = CFLRecoveryStrategy(recovery);
+      ti->prepare();
+    }
+    void get_scratch(int what, double *out) const override
+    {
+      const std::vector<double> *v = nullptr;
+      switch (what) {
+      case 0: v = &module->alpha(); break;
+      case 1: v = &module->dij(); break;
+      case 2: v = &module->lij(); break;
+      case 3: v = &module->lij_next(); break;
+      case 4: v = &module->pij(); break;
+      case 5: v = &module->r(); break;
+      case 6: v = &module->bounds(); break;
+      default: throw std::runtime_error("oracle: unknown scratch id");
+      }
+      std::memcpy(out, v->data(), v->size() * sizeof(double));
+    }
+    void counters(unsigned int *restarts, unsigned int *warnings) const override
+    {
+      *restarts = module->n_restarts();
+      *warnings = module->n_warnings();
+    }
+    double last_tau_max() const override { return module->last_tau_max(); }
+
+    /* time_loop.template.h:690-832 with all components, normalized */
+    void errors(double t, double *out3) override
+    {
+      positions_required();
+      module->prepare_state_vector(slots[0], t);
+      const unsigned int n = off->od.n_owned;
+      std::vector<double> analytic(std::size_t(n) * Sys::k);
+      for (unsigned int i = 0; i < n; ++i) {
+        const auto s = iv.initial_state(off->mesh.position(i), t);
+        for (int c = 0; c < Sys::k; ++c)
+          analytic[std::size_t(i) * Sys::k + c] = s[c];
+      }
+      double linf = 0., l1 = 0., l2 = 0.;
+      std::vector<double> a(n), e(n);
+      for (int c = 0; c < Sys::k; ++c) {
+        if (!((error_mask >> c) & 1u))
+          continue;
         for (unsigned int i = 0; i < n; ++i) {
           a[i] = analytic[std::size_t(i) * Sys::k + c];
           e[i] = slots[0].U[std::size_t(i) * Sys::k + c] - a[i];
@@ -694,6 +886,52 @@ void *orc_sim_create_euler(void *offline, const double *params, const double *iv
     });
   });
   return rc == 0 ? result : nullptr;
+}
+
+/* iv = (kind, direction[3], position[3], p[4]) */
+void *orc_sim_create_sw(void *offline, const double *params, const double *iv)
+{
+  void *result = nullptr;
+  const int rc = guarded([&] {
+    WITH_OFFLINE(offline, {
+      auto *sim = new SwSim<D>(&H, make_sw_params(params));
+      sim->iv.kind = sw::InitialStateKind(int(iv[0]));
+      for (int c = 0; c < D; ++c) {
+        sim->iv.transform.direction[c] = iv[1 + c];
+        sim->iv.transform.position[c] = iv[4 + c];
+      }
+      for (int c = 0; c < 4; ++c)
+        sim->iv.p[c] = iv[7 + c];
+      sim->finalize();
+      result = static_cast<SimBase *>(sim);
+    });
+  });
+  return rc == 0 ? result : nullptr;
+}
+
+int orc_sim_n_bounds(void *s) { return static_cast<SimBase *>(s)->n_bounds(); }
+
+void orc_sim_set_error_components(void *s, unsigned int mask) { static_cast<SimBase *>(s)->error_mask = mask; }
+
+/* tests/shallow_water/riemann_solver.cc: conserved 1D states (h, m); out = (h_i, u_i, h_j, u_j,
+ * h_star, lambda_max) */
+int orc_sw_riemann(const double *params, const double *state_i, const double *state_j, double *out)
+{
+  return guarded([&] {
+    sw::System<1> sys(make_sw_params(params));
+    sw::RiemannSolver<1> rs(sys);
+    auto rd = [&](const double *st) {
+      const double h = sys.water_depth_sharp({{st[0], st[1]}});
+      return std::array<double, 3>{{h, st[1] / h, std::sqrt(sys.prm.gravity * h)}};
+    };
+    const auto rd_i = rd(state_i), rd_j = rd(state_j);
+    out[0] = rd_i[0];
+    out[1] = rd_i[1];
+    out[2] = rd_j[0];
+    out[3] = rd_j[1];
+    out[4] = rs.compute_h_star(rd_i, rd_j);
+    out[5] = rs.compute(rd_i, rd_j);
+  });
 }
 
 void orc_sim_destroy(void *s) { delete static_cast<SimBase *>(s); }

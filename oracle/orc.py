@@ -44,6 +44,43 @@ EULER_PARAM_DEFAULTS = dict(
     expensive_bounds_check=0,
 )
 
+SW_PARAM_FIELDS = (
+    "gravity",
+    "manning_friction_coefficient",
+    "reference_water_depth",
+    "dry_state_relaxation_factor",
+    "dry_state_relaxation_small",
+    "dry_state_relaxation_large",
+    "indicator_evc_factor",
+    "limiter_iterations",
+    "limiter_newton_tolerance",
+    "limiter_newton_max_iterations",
+    "limiter_relaxation_factor",
+    "limit_on_kinetic_energy",
+    "limit_on_square_velocity",
+    "expensive_bounds_check",
+)
+
+SW_PARAM_DEFAULTS = dict(
+    gravity=9.81,
+    manning_friction_coefficient=0.0,
+    reference_water_depth=1.0,
+    dry_state_relaxation_factor=2.0e-1,
+    dry_state_relaxation_small=1.0e2,
+    dry_state_relaxation_large=1.0e4,
+    indicator_evc_factor=1.0,
+    limiter_iterations=2,
+    limiter_newton_tolerance=1.0e-10,
+    limiter_newton_max_iterations=2,
+    limiter_relaxation_factor=1.0,
+    limit_on_kinetic_energy=0,
+    limit_on_square_velocity=1,
+    expensive_bounds_check=0,
+)
+
+# shallow water initial states (same numbers as enum rj_initial_state_kind)
+SW_CIRCULAR_DAM_BREAK, SW_UNIFORM, SW_RITTER_DAM_BREAK, SW_SMOOTH_VORTEX = 16, 17, 18, 19
+
 # Boundary ids, source/discretization.h:48-123
 DO_NOTHING, PERIODIC, SLIP, NO_SLIP, DIRICHLET, DYNAMIC, DIRICHLET_MOMENTUM = range(7)
 
@@ -69,6 +106,15 @@ def euler_params(**kw):
             raise KeyError(k)
         p[k] = v
     return np.array([float(p[f]) for f in EULER_PARAM_FIELDS], dtype=np.float64)
+
+
+def sw_params(**kw):
+    p = dict(SW_PARAM_DEFAULTS)
+    for k, v in kw.items():
+        if k not in p:
+            raise KeyError(k)
+        p[k] = v
+    return np.array([float(p[f]) for f in SW_PARAM_FIELDS], dtype=np.float64)
 
 
 def _dp(a):
@@ -112,6 +158,7 @@ class Oracle:
         L.orc_offline_assemble.restype = C.c_void_p
         L.orc_offline_from_arrays.restype = C.c_void_p
         L.orc_sim_create_euler.restype = C.c_void_p
+        L.orc_sim_create_sw.restype = C.c_void_p
         L.orc_sim_last_tau_max.restype = C.c_double
         L.orc_sim_last_tau_max.argtypes = [C.c_void_p]
         self.kind = "reference-pow(VCL)" if L.orc_uses_vcl() else "port"
@@ -148,6 +195,14 @@ class Oracle:
         n = np.ascontiguousarray(n_ij, dtype=np.float64)
         self._check(self.lib.orc_euler_riemann_states(int(dim), _dp(euler_params(**prm)), _dp(a), _dp(b), _dp(n), C.byref(lam)))
         return lam.value
+
+    def sw_riemann(self, state_i, state_j, **prm):
+        """tests/shallow_water/riemann_solver.cc: conserved 1D states (h, m)"""
+        out = np.zeros(6)
+        si = np.asarray(state_i, dtype=np.float64)
+        sj = np.asarray(state_j, dtype=np.float64)
+        self._check(self.lib.orc_sw_riemann(_dp(sw_params(**prm)), _dp(si), _dp(sj), _dp(out)))
+        return dict(zip(("h_i", "u_i", "h_j", "u_j", "h_star", "lambda_max"), out.tolist()))
 
     def euler_limiter(self, dim, U, P, bounds, **prm):
         out = np.zeros(5 + 4 * 8 + 1)
@@ -300,14 +355,37 @@ class Offline:
         return Sim(self, handle)
 
 
+def _sw_sim(offline, kind=SW_UNIFORM, direction=(1.0, 0.0, 0.0), position=(1.0, 0.0, 0.0), p=(1.0, 1.0, 0.0, 0.0), **prm):
+    iv = np.zeros(11)
+    iv[0] = kind
+    iv[1:4] = list(direction) + [0.0] * (3 - len(direction))
+    iv[4:7] = list(position) + [0.0] * (3 - len(position))
+    iv[7:11] = list(p) + [0.0] * (4 - len(p))
+    handle = offline.o.lib.orc_sim_create_sw(offline.h, _dp(sw_params(**prm)), _dp(iv))
+    if not handle:
+        raise OracleError(offline.o.lib.orc_last_error().decode())
+    return Sim(offline, handle)
+
+
+Offline.sw_sim = _sw_sim
+
+
 class Sim:
     """Module + TimeIntegrator + six state-vector slots (slot 0 = the state)."""
+
+    def set_error_components(self, components):
+        """restrict errors() to the given component indices (A - TimeLoop / error quantities)"""
+        mask = 0
+        for c in components:
+            mask |= 1 << int(c)
+        self.o.lib.orc_sim_set_error_components(self.h, C.c_uint(mask))
 
     def __init__(self, offline, handle):
         self.off = offline
         self.o = offline.o
         self.h = C.c_void_p(handle)
         self.k = int(self.o.lib.orc_sim_k(self.h))
+        self.n_bounds = int(self.o.lib.orc_sim_n_bounds(self.h))
         self.n = offline.n
         self.nnz = offline.nnz
 
@@ -366,7 +444,7 @@ class Sim:
 
     def scratch(self, name):
         sizes = {"alpha": self.n, "dij": self.nnz, "lij": self.nnz, "lij_next": self.nnz,
-                 "pij": self.nnz * self.k, "r": self.n * self.k, "bounds": self.n * 3}
+                 "pij": self.nnz * self.k, "r": self.n * self.k, "bounds": self.n * self.n_bounds}
         out = np.zeros(sizes[name])
         self.o._check(self.o.lib.orc_sim_get_scratch(self.h, SCRATCH[name], _dp(out)))
         return out

@@ -40,6 +40,10 @@ namespace orc
       static constexpr int k = dim + 2;           /* problem_dimension */
       static constexpr int n_precomputed = 2;     /* (s, eta) */
       static constexpr int n_bounds = 3;          /* rho_min, rho_max, s_min */
+      static constexpr int n_initial_precomputed = 0;
+      static constexpr bool shallow_water = false;
+      static constexpr bool have_source_terms = false;
+      static constexpr bool have_high_order_flux = false;
       using state_type = std::array<double, k>;
       using flux_type = std::array<Vec<dim>, k>;
       using precomputed_type = std::array<double, n_precomputed>;
@@ -169,6 +173,14 @@ namespace orc
       {
         return density(U) > 0. && internal_energy(U) > 0. &&
                specific_entropy(U) > 0.;
+      }
+
+      /* flux_contribution(pv, ipv, i, U_i) = f(U_i), hyperbolic_system.h:1186-1205 */
+      using flux_contribution_type = std::array<Vec<dim>, k>;
+      flux_contribution_type
+      flux_contribution(const std::array<double, n_precomputed> &, const double, const state_type &U) const
+      {
+        return f(U);
       }
 
       precomputed_type precompute(const state_type &U) const

@@ -11,6 +11,7 @@
 #pragma once
 
 #include "orc_mesh.h"
+#include "orc_shallow_water.h"
 #include "orc_module.h"
 
 namespace orc
@@ -331,6 +332,96 @@ namespace orc
       }
     };
   } // namespace euler
+
+
+  namespace sw
+  {
+    /* kinds match enum rj_initial_state_kind of include/ryujin_b200.h */
+    enum class InitialStateKind { circular_dam_break = 16, uniform = 17, ritter_dam_break = 18, smooth_vortex = 19 };
+
+    template <int dim>
+    struct InitialValues {
+      using Sys = System<dim>;
+      using state_type = typename Sys::state_type;
+
+      const Sys &sys;
+      InitialStateKind kind = InitialStateKind::uniform;
+      InitialTransform<dim> transform;
+      /* circular dam break: (still water depth, radius, dam amplitude)
+       * uniform: (h, u); ritter: (time initial, left water depth)
+       * smooth vortex: (reference depth, mach number, beta) */
+      std::array<double, 4> p{{0.5, 2.5, 2.5, 0.}};
+
+      explicit InitialValues(const Sys &s)
+          : sys(s)
+      {
+      }
+
+      state_type compute(const Vec<dim> &point, double t) const
+      {
+        state_type s{};
+        switch (kind) {
+        case InitialStateKind::circular_dam_break: {
+          /* initial_state_circular_dam_break.h:45-51 (sic: compares |x|^2 with the radius) */
+          const double r = norm_square<dim>(point);
+          s[0] = (r <= p[1] ? p[2] : p[0]);
+          return s;
+        }
+        case InitialStateKind::uniform:
+          return sys.from_initial_state({{p[0], p[1]}});
+        case InitialStateKind::ritter_dam_break: {
+          /* initial_state_ritter_dam_break.h:59-80 */
+          const double g = sys.prm.gravity;
+          const double t_initial = p[0], left_depth = p[1];
+          const double x = point[0];
+          const double aL = std::sqrt(g * left_depth);
+          const double xA = -(t + t_initial) * aL;
+          const double xB = 2. * (t + t_initial) * aL;
+          const double tmp = aL - x / (2. * (t + t_initial));
+          const double h_expansion = 4. / (9. * g) * tmp * tmp;
+          const double v_expansion = 2. / 3. * (x / (t + t_initial) + aL);
+          if (x <= xA) {
+            s[0] = left_depth;
+            s[1] = 0.;
+          } else if (x <= xB) {
+            s[0] = h_expansion;
+            s[1] = h_expansion * v_expansion;
+          }
+          return s;
+        }
+        case InitialStateKind::smooth_vortex: {
+          /* initial_state_smooth_vortex.h:62-88 (dim == 2 only upstream) */
+          const double gravity = sys.prm.gravity;
+          const double depth = p[0], mach = p[1], beta = p[2];
+          double pb[2];
+          pb[0] = point[0] - mach * t;
+          pb[1] = dim >= 2 ? point[dim >= 2 ? 1 : 0] : 0.;
+          const double r_square = pb[0] * pb[0] + pb[1] * pb[1];
+          const double factor = beta / (2. * M_PI) * std::exp(0.5 - 0.5 * r_square);
+          const double h = depth - (1. / (2. * gravity)) * factor * factor;
+          const double u = mach - factor * pb[1];
+          const double v = factor * pb[0];
+          s[0] = h;
+          s[1] = h * u;
+          if constexpr (dim >= 2)
+            s[2] = h * v;
+          return s;
+        }
+        }
+        return s;
+      }
+
+      state_type initial_state(const Vec<dim> &x, double t) const
+      {
+        const auto tp = transform.point(x);
+        auto state = compute(tp, t);
+        const auto M = transform.vector(Sys::momentum(state));
+        for (int d = 0; d < dim; ++d)
+          state[1 + d] = M[d];
+        return state;
+      }
+    };
+  } // namespace sw
 
 
   /* Linf / L1 / L2 norms of the Q1 function with nodal values v over the

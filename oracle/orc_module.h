@@ -133,11 +133,13 @@ namespace orc
 
     HyperbolicModule(const OfflineData<dim> &od,
                      const System &sys,
-                     DirichletFunction initial_state)
+                     DirichletFunction initial_state,
+                     std::vector<double> initial_precomputed = {})
         : id_violation_strategy_(IDViolationStrategy::warn)
         , od_(od)
         , sys_(sys)
         , initial_state_(std::move(initial_state))
+        , initial_precomputed_(std::move(initial_precomputed))
         , cfl_(0.2)
         , n_restarts_(0)
         , n_warnings_(0)
@@ -356,17 +358,64 @@ namespace orc
             const double m_i = od_.mi[i];
             const double m_i_inv = od_.mi_inv[i];
 
-            const auto flux_i = sys_.f(U_i);
-            std::vector<typename System::flux_type> flux_iHs(stages);
-            for (int s = 0; s < stages; ++s)
-              flux_iHs[s] = sys_.f(get(stage_sv[s]->U, i));
+            using flux_contribution_type = typename System::flux_contribution_type;
+            const flux_contribution_type flux_i =
+                sys_.flux_contribution(getp(old_prec, i), ipv(i), U_i);
+            std::vector<flux_contribution_type> flux_iHs(stages);
+            state_type S_iH;
+            S_iH.fill(0.);
+            for (int s = 0; s < stages; ++s) {
+              const auto U_iHs = get(stage_sv[s]->U, i);
+              flux_iHs[s] = sys_.flux_contribution(getp(stage_sv[s]->prec, i), ipv(i), U_iHs);
+              if constexpr (System::have_source_terms) {
+                const auto S = sys_.nodal_source(getp(stage_sv[s]->prec, i), U_iHs, tau);
+                for (int c = 0; c < k; ++c)
+                  S_iH[c] += stage_weights[s] * S[c];
+              }
+            }
 
+            state_type S_i;
+            S_i.fill(0.);
             state_type F_iH;
             F_iH.fill(0.);
 
+            if constexpr (System::have_source_terms) {
+              S_i = sys_.nodal_source(getp(old_prec, i), U_i, tau);
+              for (int c = 0; c < k; ++c) {
+                S_iH[c] += weight * S_i[c];
+                U_i_new[c] += tau * S_i[c];
+                F_iH[c] += m_i * S_iH[c];
+              }
+            }
+
             limiter.reset(U_i);
 
+            state_type affine_shift;
+            affine_shift.fill(0.);
+
             const std::size_t e0 = od_.row_ptr[i];
+
+            if constexpr (System::shallow_water) {
+              for (unsigned int col_idx = 0; col_idx < row_length; ++col_idx) {
+                const std::size_t e = e0 + col_idx;
+                const unsigned int j = od_.cols[e];
+                const auto U_j = get(old_U, j);
+                const auto flux_j = sys_.flux_contribution(getp(old_prec, j), ipv(j), U_j);
+                const double d_ij = dij_[e];
+                const auto c_ij = od_.c(e);
+                const auto B_ij = sys_.affine_shift(flux_i, flux_j, c_ij, d_ij);
+                for (int c = 0; c < k; ++c)
+                  affine_shift[c] += B_ij[c];
+              }
+              for (int c = 0; c < k; ++c)
+                affine_shift[c] *= tau * m_i_inv;
+            }
+
+            if constexpr (System::have_source_terms) {
+              for (int c = 0; c < k; ++c)
+                affine_shift[c] += tau * S_i[c];
+            }
+
             for (unsigned int col_idx = 0; col_idx < row_length; ++col_idx) {
               const std::size_t e = e0 + col_idx;
               const unsigned int j = od_.cols[e];
@@ -387,38 +436,87 @@ namespace orc
                   scaled_c_ij[d] = c_ij[d] * inverse;
               }
 
-              const auto flux_j = sys_.f(U_j);
+              const auto flux_j = sys_.flux_contribution(getp(old_prec, j), ipv(j), U_j);
+              const double m_ij = od_.mij[e];
 
-              const auto flux_ij =
-                  System::flux_divergence(flux_i, flux_j, c_ij);
+              const auto flux_ij = sys_.flux_divergence(flux_i, flux_j, c_ij);
               state_type P_ij;
               for (int c = 0; c < k; ++c) {
                 U_i_new[c] += tau * m_i_inv * flux_ij[c];
                 P_ij[c] = -flux_ij[c];
               }
 
-              for (int c = 0; c < k; ++c) {
-                const double diff = U_j[c] - U_i[c];
-                U_i_new[c] += tau * m_i_inv * d_ij * diff;
-                F_iH[c] += d_ijH * diff;
-                P_ij[c] += (d_ijH - d_ij) * diff;
+              if constexpr (System::shallow_water) {
+                const auto eq = sys_.equilibrated_states(flux_i, flux_j);
+                const auto &U_star_ij = eq[0];
+                const auto &U_star_ji = eq[1];
+                for (int c = 0; c < k; ++c) {
+                  const double diff = U_star_ji[c] - U_star_ij[c];
+                  U_i_new[c] += tau * m_i_inv * d_ij * diff;
+                  F_iH[c] += d_ijH * diff;
+                  P_ij[c] += (d_ijH - d_ij) * diff;
+                }
+                limiter.accumulate(U_j, U_star_ij, U_star_ji, scaled_c_ij, affine_shift);
+              } else {
+                for (int c = 0; c < k; ++c) {
+                  const double diff = U_j[c] - U_i[c];
+                  U_i_new[c] += tau * m_i_inv * d_ij * diff;
+                  F_iH[c] += d_ijH * diff;
+                  P_ij[c] += (d_ijH - d_ij) * diff;
+                }
+                limiter.accumulate(getp(old_prec, j), U_j, scaled_c_ij);
               }
 
-              limiter.accumulate(getp(old_prec, j), U_j, scaled_c_ij);
+              if constexpr (System::have_source_terms) {
+                for (int c = 0; c < k; ++c) {
+                  F_iH[c] -= m_ij * S_iH[c];
+                  P_ij[c] -= m_ij * /*sic!*/ S_i[c];
+                }
+              }
 
-              for (int c = 0; c < k; ++c) {
-                F_iH[c] += weight * flux_ij[c];
-                P_ij[c] += weight * flux_ij[c];
+              if constexpr (System::have_high_order_flux) {
+                const auto high_order_flux_ij = sys_.high_order_flux_divergence(flux_i, flux_j, c_ij);
+                for (int c = 0; c < k; ++c) {
+                  F_iH[c] += weight * high_order_flux_ij[c];
+                  P_ij[c] += weight * high_order_flux_ij[c];
+                }
+              } else {
+                for (int c = 0; c < k; ++c) {
+                  F_iH[c] += weight * flux_ij[c];
+                  P_ij[c] += weight * flux_ij[c];
+                }
+              }
+
+              if constexpr (System::have_source_terms) {
+                const auto S_j = sys_.nodal_source(getp(old_prec, j), U_j, tau);
+                for (int c = 0; c < k; ++c) {
+                  F_iH[c] += weight * m_ij * S_j[c];
+                  P_ij[c] += weight * m_ij * S_j[c];
+                }
               }
 
               for (int s = 0; s < stages; ++s) {
                 const auto U_jHs = get(stage_sv[s]->U, j);
-                const auto flux_jHs = sys_.f(U_jHs);
-                const auto flux_ij_s =
-                    System::flux_divergence(flux_iHs[s], flux_jHs, c_ij);
-                for (int c = 0; c < k; ++c) {
-                  F_iH[c] += stage_weights[s] * flux_ij_s[c];
-                  P_ij[c] += stage_weights[s] * flux_ij_s[c];
+                const auto flux_jHs = sys_.flux_contribution(getp(stage_sv[s]->prec, j), ipv(j), U_jHs);
+                if constexpr (System::have_high_order_flux) {
+                  const auto ho = sys_.high_order_flux_divergence(flux_iHs[s], flux_jHs, c_ij);
+                  for (int c = 0; c < k; ++c) {
+                    F_iH[c] += stage_weights[s] * ho[c];
+                    P_ij[c] += stage_weights[s] * ho[c];
+                  }
+                } else {
+                  const auto flux_ij_s = sys_.flux_divergence(flux_iHs[s], flux_jHs, c_ij);
+                  for (int c = 0; c < k; ++c) {
+                    F_iH[c] += stage_weights[s] * flux_ij_s[c];
+                    P_ij[c] += stage_weights[s] * flux_ij_s[c];
+                  }
+                }
+                if constexpr (System::have_source_terms) {
+                  const auto S_js = sys_.nodal_source(getp(stage_sv[s]->prec, j), U_jHs, tau);
+                  for (int c = 0; c < k; ++c) {
+                    F_iH[c] += stage_weights[s] * m_ij * S_js[c];
+                    P_ij[c] += stage_weights[s] * m_ij * S_js[c];
+                  }
                 }
               }
 
@@ -604,6 +702,10 @@ namespace orc
     const OfflineData<dim> &od_;
     const System &sys_;
     DirichletFunction initial_state_;
+    /* initial_precomputed_ (hyperbolic_module.h:311): one value per node (bathymetry) or empty */
+    std::vector<double> initial_precomputed_;
+
+    double ipv(std::size_t i) const { return initial_precomputed_.empty() ? 0. : initial_precomputed_[i]; }
 
     mutable double cfl_;
     mutable unsigned int n_restarts_, n_warnings_;

