@@ -79,7 +79,8 @@ enum rj_initial_state_kind {
   RJ_INITIAL_ISENTROPIC_VORTEX = 2, /* euler/initial_state_isentropic_vortex.h */
   RJ_INITIAL_SW_CIRCULAR_DAM_BREAK = 16, /* shallow_water/initial_state_circular_dam_break.h */
   RJ_INITIAL_SW_UNIFORM = 17,            /* shallow_water/initial_state_uniform.h */
-  RJ_INITIAL_SW_RITTER_DAM_BREAK = 18    /* shallow_water/initial_state_ritter_dam_break.h */
+  RJ_INITIAL_SW_RITTER_DAM_BREAK = 18,   /* shallow_water/initial_state_ritter_dam_break.h */
+  RJ_INITIAL_SW_SMOOTH_VORTEX = 19       /* shallow_water/initial_state_smooth_vortex.h */
 };
 
 const char *rj_last_error(void);
@@ -254,6 +255,7 @@ typedef struct rj_equation_desc {
   double gravity;
   double manning_friction_coefficient;
   double reference_water_depth;
+  double dry_state_relaxation_factor;
   double dry_state_relaxation_small;
   double dry_state_relaxation_large;
 } rj_equation_desc;
@@ -269,6 +271,9 @@ typedef struct rj_module_params {
   /* F - HyperbolicModule/riemann solver, euler/riemann_solver.h:26-38 */
   double riemann_newton_tolerance;
   uint32_t riemann_newton_max_iterations;
+  /* shallow water limiter, shallow_water/limiter.h:42-58 */
+  int32_t limit_on_kinetic_energy;
+  int32_t limit_on_square_velocity;
 } rj_module_params;
 
 typedef struct rj_initial_values_desc {
@@ -279,7 +284,10 @@ typedef struct rj_initial_values_desc {
   double primitive[3];       /* uniform / contrast left: (rho, u, p)          */
   double primitive_right[3]; /* contrast right                                */
   double mach_number, beta;  /* isentropic vortex                             */
-  double sw_params[4];       /* shallow water states, see DESIGN.md           */
+  /* shallow water states: circular dam break (still water depth, radius, dam
+   * amplitude); uniform (h, u); ritter (time initial, left depth); smooth
+   * vortex (reference depth, mach number, beta) */
+  double sw_params[4];
 } rj_initial_values_desc;
 
 void rj_equation_desc_default(rj_equation_desc *eq, int equation);
@@ -323,6 +331,13 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
                                 rj_comm *comm,
                                 void *stream);
 void rj_hyperbolic_module_destroy(rj_hyperbolic_module *hm);
+
+/* initial_precomputed_ (hyperbolic_module.h:309; filled by
+ * InitialValues::interpolate_initial_precomputed_vector in the reference): for the
+ * shallow water equations one value per owned row, the bathymetry Z_i
+ * (shallow_water/hyperbolic_system.h:710-728).  Zero until set.  Ghost rows are
+ * exchanged here.  Returns RJ_ERR_INVALID for equations without such a vector. */
+int rj_hyperbolic_module_set_initial_precomputed(rj_hyperbolic_module *hm, const double *host_values);
 
 /* prepare_state_vector(state, t): hyperbolic_module.template.h:97-193 */
 int rj_hyperbolic_module_prepare_state_vector(rj_hyperbolic_module *hm, rj_state *state, double t);

@@ -117,6 +117,7 @@ namespace
     virtual void counters(unsigned int *restarts, unsigned int *warnings) const = 0;
     virtual double last_tau_max() const = 0;
     virtual void errors(double t, double *out3) = 0;
+    virtual void set_initial_precomputed(const double *) { throw std::runtime_error("oracle: no initial precomputed vector"); }
     unsigned int error_mask = ~0u; /* bit c: include component c in the error norms */
   };
 
@@ -328,6 +329,11 @@ namespace
     int n_bounds() const override { return Sys::n_bounds; }
     unsigned int n() const override { return off->od.n_owned; }
     std::size_t nnz() const override { return off->od.cols.size(); }
+
+    void set_initial_precomputed(const double *z) override
+    {
+      module->set_initial_precomputed(std::vector<double>(z, z + off->od.n_owned));
+    }
 
     void positions_required() const
     {
@@ -910,6 +916,11 @@ void *orc_sim_create_sw(void *offline, const double *params, const double *iv)
 }
 
 int orc_sim_n_bounds(void *s) { return static_cast<SimBase *>(s)->n_bounds(); }
+
+int orc_sim_set_initial_precomputed(void *s, const double *values)
+{
+  return guarded([&] { static_cast<SimBase *>(s)->set_initial_precomputed(values); });
+}
 
 void orc_sim_set_error_components(void *s, unsigned int mask) { static_cast<SimBase *>(s)->error_mask = mask; }
 

@@ -380,6 +380,12 @@ class Sim:
             mask |= 1 << int(c)
         self.o.lib.orc_sim_set_error_components(self.h, C.c_uint(mask))
 
+    def set_initial_precomputed(self, values):
+        """bathymetry of the shallow water equations, one value per node"""
+        z = np.ascontiguousarray(values, dtype=np.float64)
+        assert z.size == self.n
+        self.o._check(self.o.lib.orc_sim_set_initial_precomputed(self.h, _dp(z)))
+
     def __init__(self, offline, handle):
         self.off = offline
         self.o = offline.o

@@ -146,6 +146,9 @@ namespace orc
     {
     }
 
+    /* test hook: replace initial_precomputed_ (bathymetry) after construction */
+    void set_initial_precomputed(std::vector<double> v) { initial_precomputed_ = std::move(v); }
+
     void prepare()
     {
       if (sys_.prm.limiter_iterations > 2)

@@ -116,6 +116,7 @@ class EquationDesc(C.Structure):
         ("gravity", C.c_double),
         ("manning_friction_coefficient", C.c_double),
         ("reference_water_depth", C.c_double),
+        ("dry_state_relaxation_factor", C.c_double),
         ("dry_state_relaxation_small", C.c_double),
         ("dry_state_relaxation_large", C.c_double),
     ]
@@ -132,6 +133,8 @@ class ModuleParams(C.Structure):
         ("limiter_relaxation_factor", C.c_double),
         ("riemann_newton_tolerance", C.c_double),
         ("riemann_newton_max_iterations", C.c_uint32),
+        ("limit_on_kinetic_energy", C.c_int32),
+        ("limit_on_square_velocity", C.c_int32),
     ]
 
 
@@ -190,6 +193,7 @@ _SIGNATURES = {
         [C.POINTER(vp), vp, C.POINTER(EquationDesc), C.POINTER(ModuleParams), C.POINTER(InitialValuesDesc), vp, vp],
     ),
     "rj_hyperbolic_module_destroy": (None, [vp]),
+    "rj_hyperbolic_module_set_initial_precomputed": (C.c_int, [vp, vp]),
     "rj_hyperbolic_module_prepare_state_vector": (C.c_int, [vp, vp, C.c_double]),
     "rj_hyperbolic_module_step": (
         C.c_int,

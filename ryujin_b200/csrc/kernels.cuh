@@ -51,6 +51,9 @@
 #ifndef RJ_MB_LOW
 #define RJ_MB_LOW 4
 #endif
+#ifndef RJ_MB_LOW_SW
+#define RJ_MB_LOW_SW 2 /* shallow water: star states + sources need ~200 registers */
+#endif
 #ifndef RJ_MB_PIJ
 #define RJ_MB_PIJ 5
 #endif
@@ -199,6 +202,7 @@ namespace rjb
                                typename Eq::Params prm,
                                uint32_t n_relevant,
                                const double *__restrict__ U,
+                               const double *__restrict__ initial_precomputed,
                                double *__restrict__ prec,
                                double *__restrict__ aux)
   {
@@ -214,7 +218,12 @@ namespace rjb
     double U_i[k], prec_i[np], aux_i[na];
     load_state<k>(U, v.ld, i, U_i);
     Eq::precompute(prm, U_i, prec_i);
-    Eq::store_aux(Eq::flux_contribution(prm, prec_i, U_i), aux_i);
+    if constexpr (Eq::shallow_water)
+      /* flux_contribution = (U_i, Z_i): the bathymetry is the "initial precomputed"
+       * vector of the reference, shallow_water/hyperbolic_system.h:710-728 */
+      Eq::store_aux(Eq::flux_contribution(prm, prec_i, U_i, initial_precomputed[i]), aux_i);
+    else
+      Eq::store_aux(Eq::flux_contribution(prm, prec_i, U_i), aux_i);
     store_state<np>(prec, v.ld, i, prec_i);
     store_state<na>(aux, v.ld, i, aux_i);
   }
@@ -463,7 +472,7 @@ namespace rjb
    * hyperbolic_module.template.h:597-884.
    * ---------------------------------------------------------------------- */
   template <class Eq, int stages>
-  __global__ void __launch_bounds__(128, RJ_MB_LOW) k_low_order(StencilView v,
+  __global__ void __launch_bounds__(128, Eq::shallow_water ? RJ_MB_LOW_SW : RJ_MB_LOW) k_low_order(StencilView v,
                                                      typename Eq::Params prm,
                                                      uint32_t row_begin,
                                                      uint32_t row_end,
@@ -505,12 +514,27 @@ namespace rjb
 
     double U_is[stages > 0 ? stages : 1][k];
     typename Eq::Flux flux_is[stages > 0 ? stages : 1];
+    /* nodal sources, :640-672 (only equations with have_source_terms) */
+    double S_i[Eq::have_source_terms ? k : 1], S_iH[Eq::have_source_terms ? k : 1];
+    if constexpr (Eq::have_source_terms) {
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        S_iH[q] = 0.;
+    }
 #pragma unroll
     for (int s = 0; s < stages; ++s) {
       double aux_s[na];
       load_state<k>(st.U[s], v.ld, i, U_is[s]);
       load_state<na>(st.aux[s], v.ld, i, aux_s);
       flux_is[s] = Eq::load_aux(aux_s);
+      if constexpr (Eq::have_source_terms) {
+        double prec_s[np], S[k];
+        load_state<np>(st.prec[s], v.ld, i, prec_s);
+        Eq::nodal_source(prm, prec_s, U_is[s], tau, S);
+#pragma unroll
+        for (int q = 0; q < k; ++q)
+          S_iH[q] += st.weight[s] * S[q];
+      }
     }
 
     double U_i_new[k], F_iH[k];
@@ -520,10 +544,46 @@ namespace rjb
       F_iH[q] = 0.;
     }
 
+    if constexpr (Eq::have_source_terms) {
+      Eq::nodal_source(prm, prec_i, U_i, tau, S_i);
+#pragma unroll
+      for (int q = 0; q < k; ++q) {
+        S_iH[q] += weight * S_i[q];
+        U_i_new[q] += tau * S_i[q];
+        F_iH[q] += m_i * S_iH[q];
+      }
+    }
+
     typename Eq::LimiterAccumulator limiter;
     limiter.reset();
 
     const double tau_m_i_inv = tau * m_i_inv;
+
+    /* affine shift of the bar states, :700-720 (shallow water only) */
+    double affine_shift[Eq::shallow_water ? k : 1];
+    if constexpr (Eq::shallow_water) {
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        affine_shift[q] = 0.;
+      for (uint32_t col = 0; col < r.len; ++col) {
+        const uint32_t e = r.base + col * 32;
+        const uint32_t j = v.cols[e];
+        double aux_j[na], c_ij[dim], B_ij[k];
+        load_state<na>(aux, v.ld, j, aux_j);
+#pragma unroll
+        for (int d = 0; d < dim; ++d)
+          c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
+        Eq::affine_shift(prm, U_i, flux_i, Eq::load_aux(aux_j), c_ij, dij[e], B_ij);
+#pragma unroll
+        for (int q = 0; q < k; ++q)
+          affine_shift[q] += B_ij[q];
+      }
+#pragma unroll
+      for (int q = 0; q < k; ++q) {
+        affine_shift[q] *= tau * m_i_inv;
+        affine_shift[q] += tau * S_i[q];
+      }
+    }
 
     RJ_UNROLL(RJ_UNROLL_LOW)
     for (uint32_t col = 0; col < r.len; ++col) {
@@ -553,27 +613,74 @@ namespace rjb
       const typename Eq::Flux flux_j = Eq::load_aux(aux_j);
 
       double flux_ij[k], P_ij[k];
-      Eq::flux_divergence(U_i, flux_i, U_j, flux_j, c_ij, flux_ij);
+      if constexpr (Eq::shallow_water)
+        Eq::flux_divergence(prm, U_i, flux_i, U_j, flux_j, c_ij, flux_ij);
+      else
+        Eq::flux_divergence(U_i, flux_i, U_j, flux_j, c_ij, flux_ij);
 #pragma unroll
       for (int q = 0; q < k; ++q) {
         U_i_new[q] += tau_m_i_inv * flux_ij[q];
         P_ij[q] = -flux_ij[q];
       }
 
+      if constexpr (Eq::shallow_water) {
+        /* equilibrated (hydrostatically reconstructed) states, :773-800 */
+        double U_star_ij[k], U_star_ji[k];
+        Eq::star_state(prm, U_i, flux_i.Z, flux_j.Z, U_star_ij);
+        Eq::star_state(prm, U_j, flux_j.Z, flux_i.Z, U_star_ji);
 #pragma unroll
-      for (int q = 0; q < k; ++q) {
-        const double diff = U_j[q] - U_i[q];
-        U_i_new[q] += tau_m_i_inv * d_ij * diff;
-        F_iH[q] += d_ijH * diff;
-        P_ij[q] += (d_ijH - d_ij) * diff;
+        for (int q = 0; q < k; ++q) {
+          const double diff = U_star_ji[q] - U_star_ij[q];
+          U_i_new[q] += tau_m_i_inv * d_ij * diff;
+          F_iH[q] += d_ijH * diff;
+          P_ij[q] += (d_ijH - d_ij) * diff;
+        }
+        limiter.accumulate_sw(prm, U_i, U_j, U_star_ij, U_star_ji, scaled_c_ij, affine_shift);
+      } else {
+#pragma unroll
+        for (int q = 0; q < k; ++q) {
+          const double diff = U_j[q] - U_i[q];
+          U_i_new[q] += tau_m_i_inv * d_ij * diff;
+          F_iH[q] += d_ijH * diff;
+          P_ij[q] += (d_ijH - d_ij) * diff;
+        }
+        limiter.accumulate(prm, U_i, U_j, prec_j, scaled_c_ij);
       }
 
-      limiter.accumulate(prm, U_i, U_j, prec_j, scaled_c_ij);
-
+      double m_ij = 0.;
+      if constexpr (Eq::have_source_terms) {
+        m_ij = v.mij[e];
 #pragma unroll
-      for (int q = 0; q < k; ++q) {
-        F_iH[q] += weight * flux_ij[q];
-        P_ij[q] += weight * flux_ij[q];
+        for (int q = 0; q < k; ++q) {
+          F_iH[q] -= m_ij * S_iH[q];
+          P_ij[q] -= m_ij * /*sic, :812*/ S_i[q];
+        }
+      }
+
+      if constexpr (Eq::have_high_order_flux) {
+        double ho[k];
+        Eq::high_order_flux_divergence(prm, U_i, flux_i, U_j, flux_j, c_ij, ho);
+#pragma unroll
+        for (int q = 0; q < k; ++q) {
+          F_iH[q] += weight * ho[q];
+          P_ij[q] += weight * ho[q];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < k; ++q) {
+          F_iH[q] += weight * flux_ij[q];
+          P_ij[q] += weight * flux_ij[q];
+        }
+      }
+
+      if constexpr (Eq::have_source_terms) {
+        double S_j[k];
+        Eq::nodal_source(prm, prec_j, U_j, tau, S_j);
+#pragma unroll
+        for (int q = 0; q < k; ++q) {
+          F_iH[q] += weight * m_ij * S_j[q];
+          P_ij[q] += weight * m_ij * S_j[q];
+        }
       }
 
 #pragma unroll
@@ -582,11 +689,24 @@ namespace rjb
         load_state<k>(st.U[s], v.ld, j, U_js);
         load_state<na>(st.aux[s], v.ld, j, aux_js);
         const typename Eq::Flux flux_js = Eq::load_aux(aux_js);
-        Eq::flux_divergence(U_is[s], flux_is[s], U_js, flux_js, c_ij, flux_ij_s);
+        if constexpr (Eq::have_high_order_flux)
+          Eq::high_order_flux_divergence(prm, U_is[s], flux_is[s], U_js, flux_js, c_ij, flux_ij_s);
+        else
+          Eq::flux_divergence(U_is[s], flux_is[s], U_js, flux_js, c_ij, flux_ij_s);
 #pragma unroll
         for (int q = 0; q < k; ++q) {
           F_iH[q] += st.weight[s] * flux_ij_s[q];
           P_ij[q] += st.weight[s] * flux_ij_s[q];
+        }
+        if constexpr (Eq::have_source_terms) {
+          double prec_js[np], S_js[k];
+          load_state<np>(st.prec[s], v.ld, j, prec_js);
+          Eq::nodal_source(prm, prec_js, U_js, tau, S_js);
+#pragma unroll
+          for (int q = 0; q < k; ++q) {
+            F_iH[q] += st.weight[s] * m_ij * S_js[q];
+            P_ij[q] += st.weight[s] * m_ij * S_js[q];
+          }
         }
       }
 

@@ -10,6 +10,7 @@
 #include "host_offline.h"
 #include "initial_values.cuh"
 #include "kernels.cuh"
+#include "shallow_water.cuh"
 
 #include <nccl.h>
 
@@ -100,6 +101,10 @@ struct rj_hyperbolic_module {
   double *send_buffer = nullptr;
   size_t send_buffer_size = 0;
   double *staging = nullptr; /* n_owned * max(k, n_prec, n_bounds) */
+  /* initial_precomputed_ of the reference (hyperbolic_module.h:309): bathymetry for the
+   * shallow water equations, ld entries incl. ghosts, zero until set; null for Euler */
+  double *initial_precomputed = nullptr;
+  int n_initial_precomputed = 0;
   uint32_t *csr_to_sliced = nullptr;
   size_t nnz = 0;
 
@@ -155,6 +160,8 @@ struct rj_hyperbolic_module {
                          od->n_mat_send);
     alloc(send_buffer, send_buffer_size);
     alloc(staging, size_t(od->n_owned) * std::max(k, std::max(n_prec, n_bounds)));
+    if (n_initial_precomputed > 0)
+      alloc(initial_precomputed, size_t(n_initial_precomputed) * ld);
     RJ_CUDA(cudaStreamSynchronize(stream));
   }
 
@@ -321,6 +328,7 @@ rj_hyperbolic_module::~rj_hyperbolic_module()
   f(scalars);
   f(send_buffer);
   f(staging);
+  f(initial_precomputed);
   f(csr_to_sliced);
   for (auto ev : prof_events)
     cudaEventDestroy(ev);
@@ -372,6 +380,36 @@ namespace rjb
   }
 
 
+  template <int dim>
+  ShallowWaterParams make_sw_params(const rj_equation_desc &eq, const rj_module_params &mp)
+  {
+    ShallowWaterParams p;
+    p.gravity = eq.gravity;
+    p.manning_friction_coefficient = eq.manning_friction_coefficient;
+    p.reference_water_depth = eq.reference_water_depth;
+    p.dry_state_relaxation_factor = eq.dry_state_relaxation_factor;
+    p.dry_state_relaxation_small = eq.dry_state_relaxation_small;
+    p.dry_state_relaxation_large = eq.dry_state_relaxation_large;
+    p.evc_factor = mp.indicator_evc_factor;
+    p.limiter_newton_tolerance = mp.limiter_newton_tolerance;
+    p.limiter_relaxation_factor = mp.limiter_relaxation_factor;
+    p.limiter_newton_max_iterations = mp.limiter_newton_max_iterations;
+    p.limit_on_kinetic_energy = mp.limit_on_kinetic_energy;
+    p.limit_on_square_velocity = mp.limit_on_square_velocity;
+    return p;
+  }
+  template <>
+  ShallowWaterParams make_params<ShallowWater<1>>(const rj_equation_desc &eq, const rj_module_params &mp)
+  {
+    return make_sw_params<1>(eq, mp);
+  }
+  template <>
+  ShallowWaterParams make_params<ShallowWater<2>>(const rj_equation_desc &eq, const rj_module_params &mp)
+  {
+    return make_sw_params<2>(eq, mp);
+  }
+
+
   template <class Eq>
   struct ModuleImpl : rj_hyperbolic_module {
     typename Eq::Params prm;
@@ -383,6 +421,7 @@ namespace rjb
       n_prec = Eq::n_prec;
       n_bounds = Eq::n_bounds;
       n_aux = Eq::n_aux;
+      n_initial_precomputed = Eq::shallow_water ? 1 : 0;
     }
 
     /* rows [begin, end), begin multiple of 32 */
@@ -433,7 +472,7 @@ namespace rjb
       exchange_vector(state.U, Eq::k); /* C1 */
       /* precomputed values for owned AND ghost rows from the exchanged state: replaces C2 */
       tag(P_PRECOMPUTE);
-      launch(k_precompute<Eq>, od->n_relevant, 256, v, prm, od->n_relevant, state.U, state.prec, state.aux);
+      launch(k_precompute<Eq>, od->n_relevant, 256, v, prm, od->n_relevant, state.U, initial_precomputed, state.prec, state.aux);
     }
 
     template <int stages>
@@ -888,6 +927,7 @@ void rj_equation_desc_default(rj_equation_desc *eq, int equation)
   eq->gravity = 9.81;
   eq->manning_friction_coefficient = 0.;
   eq->reference_water_depth = 1.;
+  eq->dry_state_relaxation_factor = 2.e-1; /* shallow_water/hyperbolic_system.h:659 */
   eq->dry_state_relaxation_small = 1.e2;
   eq->dry_state_relaxation_large = 1.e4;
 }
@@ -901,6 +941,8 @@ void rj_module_params_default(rj_module_params *mp)
   mp->limiter_relaxation_factor = 1.;
   mp->riemann_newton_tolerance = 1.e-10;
   mp->riemann_newton_max_iterations = 0;
+  mp->limit_on_kinetic_energy = 0; /* shallow_water/limiter.h:50-57 */
+  mp->limit_on_square_velocity = 1;
 }
 
 void rj_initial_values_desc_default(rj_initial_values_desc *iv, int kind)
@@ -917,6 +959,27 @@ void rj_initial_values_desc_default(rj_initial_values_desc *iv, int kind)
   iv->primitive_right[2] = 1.;
   iv->mach_number = 2.;
   iv->beta = 5.;
+  switch (kind) {
+  case RJ_INITIAL_SW_CIRCULAR_DAM_BREAK: /* initial_state_circular_dam_break.h:30-40 */
+    iv->sw_params[0] = 0.5;
+    iv->sw_params[1] = 2.5;
+    iv->sw_params[2] = 2.5;
+    break;
+  case RJ_INITIAL_SW_UNIFORM: /* initial_state_uniform.h */
+    iv->sw_params[0] = 1.;
+    iv->sw_params[1] = 1.;
+    break;
+  case RJ_INITIAL_SW_RITTER_DAM_BREAK: /* initial_state_ritter_dam_break.h:40-48 */
+    iv->sw_params[0] = 0.1;
+    iv->sw_params[1] = 0.005;
+    break;
+  case RJ_INITIAL_SW_SMOOTH_VORTEX: /* initial_state_smooth_vortex.h:38-50 */
+    iv->sw_params[0] = 1.;
+    iv->sw_params[1] = 2.;
+    iv->sw_params[2] = 0.1;
+    break;
+  default: break;
+  }
 }
 
 /* ---- module ---- */
@@ -954,6 +1017,14 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
         make(Euler<2>());
       else
         make(Euler<3>());
+    } else if (eq->equation == RJ_EQUATION_SHALLOW_WATER) {
+      /* the reference instantiates shallow water for dim 1 and 2 */
+      if (od->dim == 1)
+        make(ShallowWater<1>());
+      else if (od->dim == 2)
+        make(ShallowWater<2>());
+      else
+        throw InvalidArgument("rj_hyperbolic_module_create: shallow water needs dim 1 or 2");
     } else
       throw InvalidArgument("rj_hyperbolic_module_create: equation module not available");
 
@@ -996,6 +1067,25 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
 }
 
 void rj_hyperbolic_module_destroy(rj_hyperbolic_module *hm) { delete hm; }
+
+int rj_hyperbolic_module_set_initial_precomputed(rj_hyperbolic_module *hm, const double *host_values)
+{
+  return guarded([&] {
+    if (!hm || !host_values)
+      throw InvalidArgument("null argument");
+    if (hm->n_initial_precomputed == 0)
+      throw InvalidArgument("this equation has no initial precomputed vector");
+    RJ_CUDA(cudaSetDevice(hm->device));
+    const int nc = hm->n_initial_precomputed;
+    const uint32_t n = hm->od->n_owned;
+    RJ_CUDA(cudaMemcpyAsync(
+        hm->staging, host_values, size_t(n) * nc * sizeof(double), cudaMemcpyHostToDevice, hm->stream));
+    hm->launch(k_aos_to_soa, size_t(n) * nc, 256, n, uint32_t(nc), hm->od->ld, hm->staging, hm->initial_precomputed);
+    hm->exchange_vector(hm->initial_precomputed, nc);
+    RJ_CUDA(cudaStreamSynchronize(hm->stream));
+    return RJ_OK;
+  });
+}
 
 int rj_hyperbolic_module_prepare_state_vector(rj_hyperbolic_module *hm, rj_state *state, double t)
 {

@@ -45,6 +45,7 @@ class InitialState(enum.IntEnum):
     sw_circular_dam_break = 16
     sw_uniform = 17
     sw_ritter_dam_break = 18
+    sw_smooth_vortex = 19
 
 
 class HyperbolicSystem:
@@ -221,6 +222,13 @@ class HyperbolicModule:
         check(lib.rj_hyperbolic_module_sizes(self._h, sizes))
         self.k, self.n_precomputed, self.n_bounds, self.n_owned, self.ld, self.n_entries = (int(x) for x in sizes)
         self.nnz = offline_data.host.nnz
+
+    def set_initial_precomputed(self, values):
+        """initial_precomputed_ of the reference (hyperbolic_module.h:309): the bathymetry for the
+        shallow water equations, one value per owned row."""
+        a = np.ascontiguousarray(values, dtype=np.float64)
+        assert a.size == self.n_owned
+        check(lib.rj_hyperbolic_module_set_initial_precomputed(self._h, a.ctypes.data))
 
     # -- reference API ---------------------------------------------------------
     def prepare_state_vector(self, state, t):

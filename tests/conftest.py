@@ -9,6 +9,12 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# The oracle and the host-side generator are OpenMP parallel, and the test problems are small:
+# on a many-core box that is shared with other jobs 64+ spinning threads per parallel region
+# cost minutes.  Must be set before libgomp is loaded.
+os.environ.setdefault("OMP_NUM_THREADS", str(min(8, os.cpu_count() or 1)))
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run with -m gpu on the B200 box)")

@@ -204,3 +204,83 @@ def rel_linf_per_component(a, b):
         scale = max(np.max(np.abs(b[:, c])), floor)
         out.append(np.max(np.abs(a[:, c] - b[:, c])) / (scale if scale > 0 else 1.0))
     return np.array(out)
+
+
+# ---------------------------------------------------------------------------------------
+# shallow water (BASELINE config 5)
+B_DYNAMIC, B_DIRICHLET_MOMENTUM, B_NO_SLIP = 5, 6, 3
+
+SW_CASES = {
+    # tests/shallow_water/verification-smooth_vortex-erk33-*.prm
+    "sw_vortex2d": dict(
+        dim=2, bottom_left=[-6.0, -6.0], top_right=[6.0, 6.0], boundary=[B_DIRICHLET] * 4,
+        iv=dict(kind="sw_smooth_vortex", direction=[1.0, 1.0], position=[-1.0, -1.0], sw_params=[2.0, 1.0, 2.0]),
+        eq=dict(gravity=9.81, reference_water_depth=2.0, dry_state_relaxation_factor=0.0),
+        mp=dict(limit_on_kinetic_energy=0, limit_on_square_velocity=1),
+    ),
+    # config 5 of BASELINE.json: 2D circular dam break, slip walls; h jumps 2.5 -> 0.5 at |x|^2 = 2.5
+    "sw_dam2d": dict(
+        dim=2, bottom_left=[-5.0, -5.0], top_right=[5.0, 5.0], boundary=[B_SLIP] * 4,
+        iv=dict(kind="sw_circular_dam_break", direction=[1.0, 0.0], position=[0.0, 0.0], sw_params=[0.5, 2.5, 2.5]),
+        eq=dict(gravity=9.81, reference_water_depth=1.0),
+        mp=dict(limit_on_kinetic_energy=0, limit_on_square_velocity=1),
+    ),
+    # both limiter branches + friction + mixed boundary ids on the same dam break
+    "sw_dam2d_friction": dict(
+        dim=2, bottom_left=[-5.0, -5.0], top_right=[5.0, 5.0],
+        boundary=[B_DYNAMIC, B_DIRICHLET_MOMENTUM, B_NO_SLIP, B_SLIP],
+        iv=dict(kind="sw_circular_dam_break", direction=[1.0, 0.0], position=[0.3, -0.2], sw_params=[0.5, 2.5, 2.5]),
+        eq=dict(gravity=9.81, reference_water_depth=1.0, manning_friction_coefficient=0.05),
+        mp=dict(limit_on_kinetic_energy=1, limit_on_square_velocity=1),
+    ),
+    # tests/shallow_water/verification-ritter_dam_break-erk33-*.prm: 1D, dry bed, kinetic-energy limiter
+    "sw_ritter1d": dict(
+        dim=1, bottom_left=[0.0], top_right=[10.0], boundary=[B_DIRICHLET] * 2,
+        iv=dict(kind="sw_ritter_dam_break", direction=[1.0], position=[5.0], sw_params=[1.0, 0.005]),
+        eq=dict(gravity=9.81, reference_water_depth=0.005, dry_state_relaxation_factor=1.0e-3),
+        mp=dict(limit_on_kinetic_energy=1, limit_on_square_velocity=0),
+    ),
+}
+
+SW_KIND_ORACLE = {
+    "sw_circular_dam_break": orc.SW_CIRCULAR_DAM_BREAK, "sw_uniform": orc.SW_UNIFORM,
+    "sw_ritter_dam_break": orc.SW_RITTER_DAM_BREAK, "sw_smooth_vortex": orc.SW_SMOOTH_VORTEX,
+}
+
+
+def make_sw_product(case, n_cells, device=0, comm=None, rank=0, n_ranks=1, **mp_extra):
+    import ryujin_b200 as rj
+
+    c = SW_CASES[case]
+    mesh = rj.CartesianMesh.rectangular_domain(c["bottom_left"], c["top_right"], n_cells, c["boundary"])
+    od = rj.OfflineData.from_mesh(mesh, rank=rank, n_ranks=n_ranks, device=device)
+    iv = dict(c["iv"])
+    kind = getattr(rj.InitialState, iv.pop("kind"))
+    mp = dict(c["mp"])
+    mp.update(mp_extra)
+    module = rj.HyperbolicModule(
+        od, rj.HyperbolicSystem(rj.Equation.shallow_water, **c["eq"]), rj.InitialValues(kind, **iv),
+        rj.ModuleParameters(**mp), comm=comm,
+    )
+    return od, module
+
+
+def make_sw_oracle(oracle, case, host, **prm_extra):
+    c = SW_CASES[case]
+    off = oracle_offline_from_host(oracle, host)
+    iv = c["iv"]
+    prm = dict(c["eq"])
+    prm.update(c["mp"])
+    prm.update(prm_extra)
+    sim = off.sw_sim(kind=SW_KIND_ORACLE[iv["kind"]], direction=iv["direction"], position=iv["position"],
+                     p=iv["sw_params"], **prm)
+    return off, sim
+
+
+def sw_bathymetry(host, amplitude=0.2):
+    """a smooth, non-trivial bathymetry at the product's node positions"""
+    x = host.positions
+    z = amplitude * np.cos(0.9 * x[:, 0])
+    if host.dim >= 2:
+        z = z * np.sin(0.7 * x[:, 1] + 0.3) + 0.05 * x[:, 1] / 5.0
+    return np.ascontiguousarray(z)
