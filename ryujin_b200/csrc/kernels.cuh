@@ -42,6 +42,18 @@
 #ifndef RJ_UNROLL_HO2
 #define RJ_UNROLL_HO2 3
 #endif
+#ifndef RJ_HO2_REVERSE
+#define RJ_HO2_REVERSE 1
+#endif
+#if RJ_HO2_REVERSE
+#define RJ_HO2_FIRST(len) ((len)-1)
+#define RJ_HO2_COND(col, len) ((col) >= 1)
+#define RJ_HO2_NEXT(col) (--(col))
+#else
+#define RJ_HO2_FIRST(len) 1
+#define RJ_HO2_COND(col, len) ((col) < (len))
+#define RJ_HO2_NEXT(col) (++(col))
+#endif
 #ifndef RJ_DIJ_W
 #define RJ_DIJ_W 4 /* warps per slice of the edge-parallel d_ij kernel */
 #endif
@@ -831,8 +843,11 @@ namespace rjb
 
     double b[nb];
     load_state<nb>(bounds, v.ld, i, b);
+    /* second sweep over the row's P_ij and l_ij in REVERSE column order: the entries read
+     * last by the first sweep are re-read first, while they are still in L2 (the per-entry
+     * results are independent, so the order is free) */
     RJ_UNROLL(RJ_UNROLL_HO2)
-    for (uint32_t col = 1; col < r.len; ++col) {
+    for (uint32_t col = RJ_HO2_FIRST(r.len); RJ_HO2_COND(col, r.len); RJ_HO2_NEXT(col)) {
       const uint32_t e = r.base + col * 32;
       const double old_l_ij = fmin(lij[e], lij[v.transposed[e]]);
       double new_p_ij[k];

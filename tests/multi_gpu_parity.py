@@ -23,16 +23,21 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import ryujin_b200 as rj  # noqa: E402
-from helpers import CASES, make_mesh, rel_linf  # noqa: E402
+from helpers import CASES, SW_CASES, make_mesh, make_sw_product, rel_linf, sw_bathymetry  # noqa: E402
 
 
 def run(case, n_cells, cycles, rank, world, comm, device, **ti_kw):
-    c = CASES[case]
-    mesh = make_mesh(case, n_cells)
-    iv = dict(c["iv"])
-    kind = getattr(rj.InitialState, iv.pop("kind"))
-    od = rj.OfflineData.from_mesh(mesh, rank=rank, n_ranks=world, device=device)
-    module = rj.HyperbolicModule(od, rj.HyperbolicSystem(), rj.InitialValues(kind, **iv), comm=comm)
+    if case in SW_CASES:
+        # shallow water with a bathymetry: also exercises the ghost exchange of initial_precomputed
+        od, module = make_sw_product(case, n_cells, device=device, comm=comm, rank=rank, n_ranks=world)
+        module.set_initial_precomputed(sw_bathymetry(od.host))
+    else:
+        c = CASES[case]
+        mesh = make_mesh(case, n_cells)
+        iv = dict(c["iv"])
+        kind = getattr(rj.InitialState, iv.pop("kind"))
+        od = rj.OfflineData.from_mesh(mesh, rank=rank, n_ranks=world, device=device)
+        module = rj.HyperbolicModule(od, rj.HyperbolicSystem(), rj.InitialValues(kind, **iv), comm=comm)
     ti = rj.TimeIntegrator(module, rj.TimeSteppingScheme.erk_33, **ti_kw)
     state = module.state_vector()
     state.interpolate(0.0)
@@ -56,6 +61,8 @@ def main():
         ("vortex3d", [24, 24, 8 * world], 10, dict(cfl_min=0.2, cfl_max=0.2, cfl_recovery_strategy=rj.CFLRecoveryStrategy.none), 2e-10),
         ("sod2d", [64, 16 * world], 20, dict(), 1e-7),
         ("sod3d", [32, 8, 8 * world], 10, dict(), 1e-7),
+        ("sw_dam2d", [48, 16 * world], 20, dict(), 1e-7),
+        ("sw_vortex2d", [32, 16 * world], 10, dict(cfl_min=0.25, cfl_max=0.25, cfl_recovery_strategy=rj.CFLRecoveryStrategy.none), 2e-10),
     ):
         od, module, U, taus = run(case, n_cells, cycles, rank, world, comm, local, **kw)
         n_global = od.host.n_global_dofs
