@@ -145,8 +145,12 @@ class Oracle:
             path = vcl if os.path.exists(vcl) else port
         elif variant == "vcl":
             path = vcl
-        else:
+        elif variant == "port":
             path = port
+        elif variant == "fma":
+            path = os.path.join(_HERE, "liboracle_fma.so")
+        else:
+            path = variant  # explicit path of another build of the same sources (experiments)
         if not os.path.exists(path):
             build(ref=(variant != "port"))
         self.path = path

@@ -47,11 +47,9 @@ def test_sw_smooth_vortex_verification(oracle):
         assert abs(err[k] - ref[k]) <= 1e-8 * ref[k], (k, err[k], ref[k])
 
 
-def test_sw_ritter_dam_break_verification(oracle):
-    """tests/shallow_water/verification-ritter_dam_break-erk33-l7: 1D, 25 * 2^7 cells on [0,10],
-    kinetic-energy limiter, error in h only."""
+def _ritter(o):
     n = 25 * 2**7
-    off = oracle.assemble([n], [0.0], [10.0 / n], [orc.DIRICHLET] * 2)
+    off = o.assemble([n], [0.0], [10.0 / n], [orc.DIRICHLET] * 2)
     assert off.n == 3201
     sim = off.sw_sim(kind=orc.SW_RITTER_DAM_BREAK, direction=(1.0,), position=(5.0,), p=(1.0, 0.005),
                      gravity=9.81, reference_water_depth=0.005, dry_state_relaxation_factor=1.0e-3,
@@ -62,12 +60,27 @@ def test_sw_ritter_dam_break_verification(oracle):
     t = 0.0
     while t < 6.0:
         t += sim.time_step(t)
-    err = sim.errors(t)
+    return t, sim.errors(t)
+
+
+def test_sw_ritter_dam_break_verification(oracle):
+    """tests/shallow_water/verification-ritter_dam_break-erk33-l7: 1D, 25 * 2^7 cells on [0,10],
+    kinetic-energy limiter, dam break over a dry bed, error in h only, 1246 cycles.
+
+    The final time (i.e. the CFL-limiting wave speeds of all cycles) is reproduced to 1e-13.  The
+    error norms of this case are sensitive to round-off at the 1e-4 level (wet/dry front): the same
+    restatement built with FP contraction (what GCC does for the reference on an AVX2/FMA host,
+    oracle/liboracle_fma.so) moves them by 1e-4 and lands within 1e-5 of the golden, the
+    contraction-free build within 1.1e-4.  The golden therefore pins the restatement to within the
+    spread of two builds of the same sources, which is what is asserted."""
     ref = dict(t=6.002065094435738, Linf=0.001137142985470178, L1=2.034821089657167e-05, L2=6.232030880580931e-05)
-    print(t, err)
-    # final time (i.e. the CFL-limiting wave speeds of all 1246 cycles) to 1e-13; the error norms
-    # agree to 1.2e-4 relative only: a residual deviation in the non-default kinetic-energy /
-    # dry-state branch that is NOT explained yet (open items)
+    t, err = _ritter(oracle)
+    t_fma, err_fma = _ritter(orc.Oracle("fma"))
+    print(t, err, t_fma, err_fma)
     assert abs(t - ref["t"]) <= 1e-13 * ref["t"]
+    assert abs(t_fma - ref["t"]) <= 1e-13 * ref["t"]
     for k in ("Linf", "L1", "L2"):
+        spread = abs(err[k] - err_fma[k])
+        assert abs(err_fma[k] - ref[k]) <= 2e-5 * ref[k], (k, err_fma[k], ref[k])
+        assert abs(err[k] - ref[k]) <= 2.0 * spread + 1e-8 * ref[k], (k, err[k], err_fma[k], ref[k])
         assert abs(err[k] - ref[k]) <= 2e-4 * ref[k], (k, err[k], ref[k])
