@@ -405,6 +405,20 @@ void rj_time_integrator_destroy(rj_time_integrator *ti);
 int rj_time_integrator_step(rj_time_integrator *ti, rj_state *state, double t, double t_final, double *tau_out);
 double rj_time_integrator_efficiency(const rj_time_integrator *ti);
 
+/* How a cycle is driven (results are bit-identical):
+ *   RJ_STEPPING_HOST    the reference's control flow, tau and the violation flag return to the host
+ *                       after every step() (time_integrator.template.h:302-443);
+ *   RJ_STEPPING_DEVICE  the whole cycle is enqueued back to back; tau, t + c tau and the flags stay
+ *                       in device memory; one synchronisation per cycle;
+ *   RJ_STEPPING_GRAPH   as DEVICE, captured into CUDA graphs (cached per state-pointer permutation)
+ *                       and replayed (default; falls back to DEVICE while profiling is on).
+ * The environment variable RYUJIN_B200_STEPPING = host | device | graph overrides the default. */
+enum rj_stepping { RJ_STEPPING_HOST = 0, RJ_STEPPING_DEVICE = 1, RJ_STEPPING_GRAPH = 2 };
+int rj_time_integrator_set_stepping(rj_time_integrator *ti, int stepping);
+int rj_time_integrator_stepping(const rj_time_integrator *ti);
+/* stats = {graphs captured, graph launches} */
+int rj_time_integrator_graph_stats(const rj_time_integrator *ti, uint64_t stats[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ from .hyperbolic_module import (  # noqa: F401
     InitialValues,
     ModuleParameters,
     StateVector,
+    Stepping,
     TimeIntegrator,
     TimeSteppingScheme,
 )

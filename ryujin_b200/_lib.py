@@ -215,6 +215,9 @@ _SIGNATURES = {
     "rj_time_integrator_destroy": (None, [vp]),
     "rj_time_integrator_step": (C.c_int, [vp, vp, C.c_double, C.c_double, f64p]),
     "rj_time_integrator_efficiency": (C.c_double, [vp]),
+    "rj_time_integrator_set_stepping": (C.c_int, [vp, C.c_int]),
+    "rj_time_integrator_stepping": (C.c_int, [vp]),
+    "rj_time_integrator_graph_stats": (C.c_int, [vp, u64p]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

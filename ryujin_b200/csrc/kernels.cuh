@@ -97,6 +97,17 @@ namespace rjb
     int numeric_error;
   };
 
+  /* device scalars of one TimeIntegrator cycle (device-resident stepping: the substeps of a
+   * cycle are enqueued without host round trips, time_integrator.template.h:302-443) */
+  constexpr int max_substeps = 8;
+  struct CycleScalars {
+    double t;       /* time at the start of the cycle            */
+    double tau_max; /* t_final - t (DBL_MAX if unbounded)        */
+    double tau;     /* step size fixed by the first substep      */
+    int restart[max_substeps];
+    int numeric_error[max_substeps];
+  };
+
   template <int n>
   struct StagePointers {
     const double *U[n > 0 ? n : 1];
@@ -154,13 +165,18 @@ namespace rjb
                                               uint32_t ld,
                                               typename Eq::Params prm,
                                               IV iv,
-                                              double t,
+                                              double t_host,
+                                              const CycleScalars *__restrict__ cycle,
+                                              double tau_factor,
                                               double *__restrict__ U)
   {
     constexpr int k = Eq::k, dim = Eq::dim;
     const uint32_t gidx = blockIdx.x * blockDim.x + threadIdx.x;
     if (gidx >= n_groups)
       return;
+    /* t + c * tau exactly as the host computes it (time_integrator.template.h:380,395) */
+    const double t =
+        cycle ? (tau_factor == 0. ? cycle->t : __dadd_rn(cycle->t, __dmul_rn(tau_factor, cycle->tau))) : t_host;
     const uint32_t i = group_dof[gidx];
     double U_i[k];
     load_state<k>(U, ld, i, U_i);
@@ -461,21 +477,46 @@ namespace rjb
     s->numeric_error = 0;
   }
 
+  /* Where a substep takes tau and tau_max from: host values (the reference API), or the
+   * device scalars of the running cycle. */
+  struct TauSource {
+    int mode;       /* 0: host values; 1: first substep of a cycle (tau = 0, tau_max = cycle->tau_max /
+                       divisor); 2: later substep (tau = cycle->tau, tau_max unbounded) */
+    double tau;     /* mode 0 */
+    double tau_max; /* mode 0 */
+    double divisor; /* mode 1 */
+  };
+
   /* local minimum -> tau_max (before the all-reduce over ranks) */
-  __global__ void k_tau_local(StepScalars *s, double tau_max_in)
+  __global__ void k_tau_local(StepScalars *s, TauSource src, const CycleScalars *cycle)
   {
     const double local = __longlong_as_double((long long)s->tau_max_bits);
     /* tau_max_bits == 0 encodes NaN or a non-positive value */
+    double tau_max_in = src.tau_max;
+    if (src.mode == 1)
+      tau_max_in = cycle->tau_max == DBL_MAX ? DBL_MAX : __ddiv_rn(cycle->tau_max, src.divisor);
+    else if (src.mode == 2)
+      tau_max_in = DBL_MAX;
     s->tau_max = fmin(local, tau_max_in);
   }
 
-  /* :571-578 */
-  __global__ void k_tau_finalize(StepScalars *s, double tau_in)
+  /* :571-578; in cycle mode also records the substep's tau */
+  __global__ void k_tau_finalize(StepScalars *s, TauSource src, CycleScalars *cycle)
   {
     const double tau_max = s->tau_max;
     if (isnan(tau_max) || isinf(tau_max) || !(tau_max > 0.))
       s->numeric_error = 1;
+    const double tau_in = src.mode == 0 ? src.tau : (src.mode == 1 ? 0. : cycle->tau);
     s->tau = (tau_in == 0. ? tau_max : tau_in);
+    if (src.mode == 1)
+      cycle->tau = s->tau;
+  }
+
+  /* end of a substep in cycle mode: keep its flags for the host's post-mortem */
+  __global__ void k_cycle_record(const StepScalars *s, CycleScalars *cycle, int substep)
+  {
+    cycle->restart[substep] = s->restart_needed;
+    cycle->numeric_error[substep] = s->numeric_error;
   }
 
 

@@ -15,6 +15,7 @@
 #include <nccl.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -109,15 +110,54 @@ struct rj_hyperbolic_module {
   size_t nnz = 0;
 
   virtual ~rj_hyperbolic_module();
-  virtual void prepare_state_vector(rj_state &state, double t) = 0;
-  virtual int step(const rj_state &old_state,
-                   int stages,
-                   const rj_state *const *stage_states,
-                   const double *stage_weights,
-                   rj_state &new_state,
-                   double tau,
-                   double tau_max,
-                   double *tau_out) = 0;
+  /* cycle != nullptr: t = cycle->t + tau_factor * cycle->tau, evaluated on the device */
+  virtual void prepare_state_vector(rj_state &state, double t, const CycleScalars *cycle = nullptr, double tau_factor = 0.) = 0;
+  /* enqueue all kernels and exchanges of one update on the stream; no host synchronisation */
+  virtual void enqueue_step(const rj_state &old_state,
+                            int stages,
+                            const rj_state *const *stage_states,
+                            const double *stage_weights,
+                            rj_state &new_state,
+                            TauSource tau_source,
+                            CycleScalars *cycle,
+                            int substep) = 0;
+
+  /* the reference call: enqueue, wait, evaluate the flags (hyperbolic_module.template.h:571-578,1190-1210) */
+  int step(const rj_state &old_state,
+           int stages,
+           const rj_state *const *stage_states,
+           const double *stage_weights,
+           rj_state &new_state,
+           double tau,
+           double tau_max,
+           double *tau_out)
+  {
+    TauSource src{0, tau, tau_max, 1.};
+    enqueue_step(old_state, stages, stage_states, stage_weights, new_state, src, nullptr, 0);
+    RJ_CUDA(cudaMemcpyAsync(h_scalars, scalars, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
+    RJ_CUDA(cudaStreamSynchronize(stream));
+    if (profiling)
+      collect_profile();
+    if (h_scalars->numeric_error)
+      throw NumericError("I'm sorry, Dave. I'm afraid I can't do that.\nWe crashed. "
+                         "(tau_max is nan, inf or not positive)");
+    *tau_out = h_scalars->tau;
+    return account_violation(h_scalars->restart_needed != 0);
+  }
+
+  /* IDViolationStrategy, hyperbolic_module.template.h:1190-1210 */
+  int account_violation(bool restart_needed)
+  {
+    if (restart_needed) {
+      if (strategy == RJ_STRATEGY_WARN)
+        n_warnings++;
+      else {
+        n_restarts++;
+        return RJ_RESTART;
+      }
+    }
+    return RJ_OK;
+  }
   virtual void interpolate(rj_state &state, double t) = 0;
 
   StencilView view() const
@@ -449,7 +489,7 @@ namespace rjb
     }
 
     /* hyperbolic_module.template.h:97-193 */
-    void prepare_state_vector(rj_state &state, double t) override
+    void prepare_state_vector(rj_state &state, double t, const CycleScalars *cycle, double tau_factor) override
     {
       RJ_CUDA(cudaSetDevice(od->device));
       const StencilView v = view();
@@ -467,6 +507,8 @@ namespace rjb
              prm,
              iv,
              t,
+             cycle,
+             tau_factor,
              state.U);
       tag(P_OTHER);
       exchange_vector(state.U, Eq::k); /* C1 */
@@ -509,14 +551,14 @@ namespace rjb
     }
 
     /* hyperbolic_module.template.h:236-1211 */
-    int step(const rj_state &old_state,
-             int stages,
-             const rj_state *const *stage_states,
-             const double *stage_weights,
-             rj_state &new_state,
-             double tau,
-             double tau_max_in,
-             double *tau_out) override
+    void enqueue_step(const rj_state &old_state,
+                      int stages,
+                      const rj_state *const *stage_states,
+                      const double *stage_weights,
+                      rj_state &new_state,
+                      TauSource tau_source,
+                      CycleScalars *cycle,
+                      int substep) override
     {
       RJ_CUDA(cudaSetDevice(od->device));
       if (stages < 0 || stages > 4)
@@ -560,11 +602,11 @@ namespace rjb
       tag(P_DII_TAU);
       launch_rows(k_dii_tau, 0, n_owned, v, 0u, n_owned, cfl, dij, scalars);
       tag(P_OTHER);
-      launch(k_tau_local, 1, 1, scalars, tau_max_in);
+      launch(k_tau_local, 1, 1, scalars, tau_source, (const CycleScalars *)cycle);
       if (comm && comm->n_ranks > 1)
         RJ_NCCL(ncclAllReduce(
             &scalars->tau_max, &scalars->tau_max, 1, ncclDouble, ncclMin, comm->comm, stream));
-      launch(k_tau_finalize, 1, 1, scalars, tau);
+      launch(k_tau_finalize, 1, 1, scalars, tau_source, cycle);
 
       /* Step 4: low-order update, bounds, r_i, P_ij; C6 */
       tag(P_LOW_ORDER);
@@ -611,49 +653,125 @@ namespace rjb
                               ncclMax,
                               comm->comm,
                               stream));
-      RJ_CUDA(cudaMemcpyAsync(h_scalars, scalars, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
-      RJ_CUDA(cudaStreamSynchronize(stream));
-      if (profiling)
-        collect_profile();
-
-      if (h_scalars->numeric_error)
-        throw NumericError("I'm sorry, Dave. I'm afraid I can't do that.\nWe crashed. "
-                           "(tau_max is nan, inf or not positive)");
-      *tau_out = h_scalars->tau;
-
-      if (h_scalars->restart_needed) {
-        if (strategy == RJ_STRATEGY_WARN)
-          n_warnings++;
-        else {
-          n_restarts++;
-          return RJ_RESTART;
-        }
-      }
-      return RJ_OK;
+      if (cycle)
+        launch(k_cycle_record, 1, 1, (const StepScalars *)scalars, cycle, substep);
     }
   };
 
 
-  /* TimeIntegrator, source/time_integrator.template.h:207-443 */
-  struct TimeIntegrator {
-    rj_hyperbolic_module *hm;
-    int scheme;
-    double cfl_min, cfl_max;
-    int recovery;
+  /* ---------------------------------------------------------------------- *
+   * TimeIntegrator, source/time_integrator.template.h:207-443.
+   *
+   * A scheme is a short program over the state slots {0 = the caller's state, 1.. = temp_}:
+   * PREPARE(slot, c) = prepare_state_vector(slot, t + c tau); STEP = HyperbolicModule::step with
+   * stage slots / weights; SADD = the convex combinations of the SSPRK schemes.  The same
+   * program runs in three ways:
+   *   host    the reference's control flow: every step() returns tau and the violation flag to
+   *           the host (one synchronisation per substep);
+   *   device  the whole cycle is enqueued back to back: tau, t + c tau and the per-substep flags
+   *           stay in device memory (CycleScalars), the host synchronises once per cycle;
+   *   graph   the enqueued cycle is captured into a CUDA graph (kernels, NCCL exchanges, the two
+   *           small copies) and replayed; graphs are cached per state-pointer permutation.
+   * All three are bit-identical: the device evaluates t + c tau and tau_max / n with the same
+   * IEEE operations as the host.
+   * ---------------------------------------------------------------------- */
+  struct Op {
+    enum Kind { PREPARE, STEP, SADD } kind;
+    int a = 0, b = 0;           /* PREPARE: slot a; STEP: old a -> new b; SADD: dst a, src b */
+    double c = 0., d = 0.;      /* PREPARE: time factor c; SADD: dst = c dst + d src */
+    std::vector<int> stages;    /* STEP */
+    std::vector<double> weights;
+    double divisor = 0.;        /* STEP: > 0 marks the first step of the cycle (tau_max / divisor) */
+  };
+
+  struct Scheme {
+    std::vector<Op> program;
+    int result_slot = 0; /* swapped with slot 0 at the end */
+    double tau_multiplier = 1.;
+    int n_temp = 0;
     double efficiency = 1.;
+  };
+
+  inline Op prepare(int slot, double c) { Op o; o.kind = Op::PREPARE; o.a = slot; o.c = c; return o; }
+  inline Op first_step(int from, int to, double divisor) { Op o; o.kind = Op::STEP; o.a = from; o.b = to; o.divisor = divisor; return o; }
+  inline Op next_step(int from, int to, std::vector<int> st = {}, std::vector<double> w = {})
+  {
+    Op o; o.kind = Op::STEP; o.a = from; o.b = to; o.stages = std::move(st); o.weights = std::move(w); return o;
+  }
+  inline Op sadd(int dst, double c, double d, int src) { Op o; o.kind = Op::SADD; o.a = dst; o.b = src; o.c = c; o.d = d; return o; }
+
+  inline Scheme make_scheme(int scheme)
+  {
+    Scheme s;
+    switch (scheme) { /* time_integrator.template.h:87-137 (storage) and :302-443 (steps) */
+    case RJ_SSPRK_22:
+      s.program = {prepare(0, 0.), first_step(0, 1, 1.), prepare(1, 1.0), next_step(1, 2), sadd(2, 1.0 / 2.0, 1.0 / 2.0, 0)};
+      s.result_slot = 2; s.n_temp = 2; s.tau_multiplier = 1.; s.efficiency = 1.;
+      break;
+    case RJ_SSPRK_33:
+      s.program = {prepare(0, 0.), first_step(0, 1, 1.), prepare(1, 1.0), next_step(1, 2), sadd(2, 1.0 / 4.0, 3.0 / 4.0, 0),
+                   prepare(2, 0.5), next_step(2, 1), sadd(1, 2.0 / 3.0, 1.0 / 3.0, 0)};
+      s.result_slot = 1; s.n_temp = 2; s.tau_multiplier = 1.; s.efficiency = 1.;
+      break;
+    case RJ_ERK_11:
+      s.program = {prepare(0, 0.), first_step(0, 1, 1.)};
+      s.result_slot = 1; s.n_temp = 1; s.tau_multiplier = 1.; s.efficiency = 1.;
+      break;
+    case RJ_ERK_22:
+      s.program = {prepare(0, 0.), first_step(0, 1, 2.), prepare(1, 1.0), next_step(1, 2, {0}, {-1.})};
+      s.result_slot = 2; s.n_temp = 2; s.tau_multiplier = 2.; s.efficiency = 2.;
+      break;
+    case RJ_ERK_33:
+      s.program = {prepare(0, 0.), first_step(0, 1, 3.), prepare(1, 1.0), next_step(1, 2, {0}, {-1.}),
+                   prepare(2, 2.0), next_step(2, 3, {0, 1}, {0.75, -2.})};
+      s.result_slot = 3; s.n_temp = 3; s.tau_multiplier = 3.; s.efficiency = 3.;
+      break;
+    case RJ_ERK_43:
+      s.program = {prepare(0, 0.), first_step(0, 1, 4.), prepare(1, 1.0), next_step(1, 2, {0}, {-1.}),
+                   prepare(2, 2.0), next_step(2, 3, {1}, {-1.}), prepare(3, 3.0),
+                   next_step(3, 4, {1, 2}, {5. / 3., -10. / 3.})};
+      s.result_slot = 4; s.n_temp = 4; s.tau_multiplier = 4.; s.efficiency = 4.;
+      break;
+    default: throw InvalidArgument("unknown time stepping scheme");
+    }
+    return s;
+  }
+
+  enum Stepping { STEPPING_HOST = 0, STEPPING_DEVICE = 1, STEPPING_GRAPH = 2 };
+
+  struct TimeIntegrator {
+    rj_hyperbolic_module *hm = nullptr;
+    int scheme_id = 0;
+    Scheme scheme;
+    double cfl_min = 0., cfl_max = 0.;
+    int recovery = 0;
+    int stepping = STEPPING_GRAPH;
     std::vector<rj_state *> temp;
 
-    double t = 0.;
+    CycleScalars *d_cycle = nullptr;
+    CycleScalars *h_cycle = nullptr; /* pinned: [0] input (t, tau_max), [1] result */
 
-    int hstep(const rj_state &old_state,
-              std::vector<const rj_state *> st,
-              std::vector<double> w,
-              rj_state &new_state,
-              double tau,
-              double tau_max,
-              double &tau_out)
+    struct CachedGraph {
+      std::vector<const void *> key;
+      cudaGraphExec_t exec = nullptr;
+      uint64_t launches = 0;
+    };
+    std::vector<CachedGraph> graphs;
+    uint64_t graph_replays = 0, graph_captures = 0;
+
+    rj_state &slot(rj_state &sv, int n) { return n == 0 ? sv : *temp[n - 1]; }
+
+    ~TimeIntegrator()
     {
-      return hm->step(old_state, int(st.size()), st.data(), w.data(), new_state, tau, tau_max, &tau_out);
+      if (hm)
+        cudaSetDevice(hm->device);
+      for (auto &g : graphs)
+        if (g.exec)
+          cudaGraphExecDestroy(g.exec);
+      if (d_cycle)
+        cudaFree(d_cycle);
+      if (h_cycle)
+        cudaFreeHost(h_cycle);
     }
   };
 } // namespace rjb
@@ -665,81 +783,148 @@ namespace rjb
 {
   constexpr double no_tau_max = DBL_MAX;
 
+  /* the reference's control flow: one host round trip per substep */
+  int single_step_host(rj_time_integrator &ti, rj_state &sv, double t, double tau_max, double &tau_out)
+  {
+    auto &hm = *ti.hm;
+    double tau = 0.;
+    for (const Op &op : ti.scheme.program) {
+      switch (op.kind) {
+      case Op::PREPARE: hm.prepare_state_vector(ti.slot(sv, op.a), op.c == 0. ? t : t + op.c * tau); break;
+      case Op::SADD: rj_state_sadd(&ti.slot(sv, op.a), op.c, op.d, &ti.slot(sv, op.b)); break;
+      case Op::STEP: {
+        std::vector<const rj_state *> st;
+        for (int q : op.stages)
+          st.push_back(&ti.slot(sv, q));
+        double out = 0.;
+        const bool first = op.divisor > 0.;
+        const int rc = hm.step(ti.slot(sv, op.a),
+                               int(st.size()),
+                               st.data(),
+                               op.weights.data(),
+                               ti.slot(sv, op.b),
+                               first ? 0. : tau,
+                               first ? tau_max / op.divisor : no_tau_max,
+                               &out);
+        if (rc != RJ_OK)
+          return rc;
+        if (first)
+          tau = out;
+      } break;
+      }
+    }
+    rj_state_swap(&sv, &ti.slot(sv, ti.scheme.result_slot));
+    tau_out = ti.scheme.tau_multiplier * tau;
+    return RJ_OK;
+  }
+
+  /* enqueue one whole cycle; returns the number of STEP ops */
+  int enqueue_cycle(rj_time_integrator &ti, rj_state &sv)
+  {
+    auto &hm = *ti.hm;
+    /* (t, tau_max) of this cycle: first 16 bytes of the pinned input block */
+    RJ_CUDA(cudaMemcpyAsync(ti.d_cycle, &ti.h_cycle[0], 2 * sizeof(double), cudaMemcpyHostToDevice, hm.stream));
+    int substep = 0;
+    for (const Op &op : ti.scheme.program) {
+      switch (op.kind) {
+      case Op::PREPARE: hm.prepare_state_vector(ti.slot(sv, op.a), 0., ti.d_cycle, op.c); break;
+      case Op::SADD: rj_state_sadd(&ti.slot(sv, op.a), op.c, op.d, &ti.slot(sv, op.b)); break;
+      case Op::STEP: {
+        std::vector<const rj_state *> st;
+        for (int q : op.stages)
+          st.push_back(&ti.slot(sv, q));
+        TauSource src{op.divisor > 0. ? 1 : 2, 0., 0., op.divisor > 0. ? op.divisor : 1.};
+        hm.enqueue_step(ti.slot(sv, op.a), int(st.size()), st.data(), op.weights.data(), ti.slot(sv, op.b), src, ti.d_cycle, substep);
+        ++substep;
+      } break;
+      }
+    }
+    RJ_CUDA(cudaMemcpyAsync(&ti.h_cycle[1], ti.d_cycle, sizeof(CycleScalars), cudaMemcpyDeviceToHost, hm.stream));
+    return substep;
+  }
+
+  int single_step_device(rj_time_integrator &ti, rj_state &sv, double t, double tau_max, double &tau_out)
+  {
+    auto &hm = *ti.hm;
+    RJ_CUDA(cudaSetDevice(hm.device));
+    ti.h_cycle[0].t = t;
+    ti.h_cycle[0].tau_max = tau_max;
+    int n_steps = 0;
+    for (const Op &op : ti.scheme.program)
+      n_steps += op.kind == Op::STEP;
+
+    const bool use_graph = ti.stepping == STEPPING_GRAPH && !hm.profiling;
+    if (!use_graph)
+      enqueue_cycle(ti, sv);
+    else {
+      /* a graph is valid for one permutation of the state pointers, one cfl and one device */
+      std::vector<const void *> key;
+      key.push_back(sv.U);
+      for (auto *s : ti.temp)
+        key.push_back(s->U);
+      uint64_t cfl_bits;
+      std::memcpy(&cfl_bits, &hm.cfl, sizeof(cfl_bits));
+      key.push_back(reinterpret_cast<const void *>(cfl_bits));
+      TimeIntegrator::CachedGraph *hit = nullptr;
+      for (auto &g : ti.graphs)
+        if (g.key == key)
+          hit = &g;
+      if (!hit) {
+        if (ti.graphs.size() >= 32) { /* pointer permutations are periodic; this is a safety net */
+          for (auto &g : ti.graphs)
+            cudaGraphExecDestroy(g.exec);
+          ti.graphs.clear();
+        }
+        const uint64_t launches_before = hm.launches;
+        cudaGraph_t graph = nullptr;
+        RJ_CUDA(cudaStreamBeginCapture(hm.stream, cudaStreamCaptureModeRelaxed));
+        try {
+          enqueue_cycle(ti, sv);
+        } catch (...) {
+          cudaStreamEndCapture(hm.stream, &graph);
+          if (graph)
+            cudaGraphDestroy(graph);
+          throw;
+        }
+        RJ_CUDA(cudaStreamEndCapture(hm.stream, &graph));
+        TimeIntegrator::CachedGraph g;
+        g.key = key;
+        g.launches = hm.launches - launches_before;
+        hm.launches = launches_before;
+        RJ_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+        RJ_CUDA(cudaGraphDestroy(graph));
+        ti.graphs.push_back(g);
+        hit = &ti.graphs.back();
+        ti.graph_captures++;
+      }
+      RJ_CUDA(cudaGraphLaunch(hit->exec, hm.stream));
+      hm.launches += hit->launches;
+      ti.graph_replays++;
+    }
+    RJ_CUDA(cudaStreamSynchronize(hm.stream));
+    if (hm.profiling)
+      hm.collect_profile();
+
+    /* the flags in the order the reference would have met them */
+    const CycleScalars &res = ti.h_cycle[1];
+    for (int q = 0; q < n_steps; ++q) {
+      if (res.numeric_error[q])
+        throw NumericError("I'm sorry, Dave. I'm afraid I can't do that.\nWe crashed. "
+                           "(tau_max is nan, inf or not positive)");
+      if (hm.account_violation(res.restart[q] != 0) != RJ_OK)
+        return RJ_RESTART; /* the reference stops here; what the later substeps computed is dropped */
+    }
+    rj_state_swap(&sv, &ti.slot(sv, ti.scheme.result_slot));
+    tau_out = ti.scheme.tau_multiplier * res.tau;
+    return RJ_OK;
+  }
+
   /* Each scheme returns RJ_OK / RJ_RESTART and the total step in tau_out. */
   int single_step(rj_time_integrator &ti, rj_state &sv, double t, double tau_max, double &tau_out)
   {
-    auto &hm = *ti.hm;
-    auto &T = ti.temp;
-    double tau = 0., dummy = 0.;
-    int rc;
-#define RJ_TRY(expr)                                                                               \
-  do {                                                                                             \
-    rc = (expr);                                                                                   \
-    if (rc != RJ_OK)                                                                               \
-      return rc;                                                                                   \
-  } while (0)
-
-    switch (ti.scheme) {
-    case RJ_SSPRK_22:
-      hm.prepare_state_vector(sv, t);
-      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max, tau));
-      hm.prepare_state_vector(*T[0], t + 1.0 * tau);
-      RJ_TRY(ti.hstep(*T[0], {}, {}, *T[1], tau, no_tau_max, dummy));
-      rj_state_sadd(T[1], 1.0 / 2.0, 1.0 / 2.0, &sv);
-      rj_state_swap(&sv, T[1]);
-      tau_out = tau;
-      return RJ_OK;
-    case RJ_SSPRK_33:
-      hm.prepare_state_vector(sv, t);
-      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max, tau));
-      hm.prepare_state_vector(*T[0], t + 1.0 * tau);
-      RJ_TRY(ti.hstep(*T[0], {}, {}, *T[1], tau, no_tau_max, dummy));
-      rj_state_sadd(T[1], 1.0 / 4.0, 3.0 / 4.0, &sv);
-      hm.prepare_state_vector(*T[1], t + 0.5 * tau);
-      RJ_TRY(ti.hstep(*T[1], {}, {}, *T[0], tau, no_tau_max, dummy));
-      rj_state_sadd(T[0], 2.0 / 3.0, 1.0 / 3.0, &sv);
-      rj_state_swap(&sv, T[0]);
-      tau_out = tau;
-      return RJ_OK;
-    case RJ_ERK_11:
-      hm.prepare_state_vector(sv, t);
-      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max, tau));
-      rj_state_swap(&sv, T[0]);
-      tau_out = tau;
-      return RJ_OK;
-    case RJ_ERK_22:
-      hm.prepare_state_vector(sv, t);
-      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max / 2., tau));
-      hm.prepare_state_vector(*T[0], t + 1.0 * tau);
-      RJ_TRY(ti.hstep(*T[0], {&sv}, {-1.}, *T[1], tau, no_tau_max, dummy));
-      rj_state_swap(&sv, T[1]);
-      tau_out = 2. * tau;
-      return RJ_OK;
-    case RJ_ERK_33:
-      hm.prepare_state_vector(sv, t);
-      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max / 3., tau));
-      hm.prepare_state_vector(*T[0], t + 1.0 * tau);
-      RJ_TRY(ti.hstep(*T[0], {&sv}, {-1.}, *T[1], tau, no_tau_max, dummy));
-      hm.prepare_state_vector(*T[1], t + 2.0 * tau);
-      RJ_TRY(ti.hstep(*T[1], {&sv, T[0]}, {0.75, -2.}, *T[2], tau, no_tau_max, dummy));
-      rj_state_swap(&sv, T[2]);
-      tau_out = 3. * tau;
-      return RJ_OK;
-    case RJ_ERK_43:
-      hm.prepare_state_vector(sv, t);
-      RJ_TRY(ti.hstep(sv, {}, {}, *T[0], 0., tau_max / 4., tau));
-      hm.prepare_state_vector(*T[0], t + 1.0 * tau);
-      RJ_TRY(ti.hstep(*T[0], {&sv}, {-1.}, *T[1], tau, no_tau_max, dummy));
-      hm.prepare_state_vector(*T[1], t + 2.0 * tau);
-      RJ_TRY(ti.hstep(*T[1], {T[0]}, {-1.}, *T[2], tau, no_tau_max, dummy));
-      hm.prepare_state_vector(*T[2], t + 3.0 * tau);
-      RJ_TRY(ti.hstep(*T[2], {T[0], T[1]}, {5. / 3., -10. / 3.}, *T[3], tau, no_tau_max, dummy));
-      rj_state_swap(&sv, T[3]);
-      tau_out = 4. * tau;
-      return RJ_OK;
-    }
-#undef RJ_TRY
-    throw InvalidArgument("rj_time_integrator_step: unknown time stepping scheme");
+    if (ti.stepping == STEPPING_HOST)
+      return single_step_host(ti, sv, t, tau_max, tau_out);
+    return single_step_device(ti, sv, t, tau_max, tau_out);
   }
 } // namespace rjb
 
@@ -1398,21 +1583,21 @@ int rj_time_integrator_create(rj_time_integrator **out,
       throw InvalidArgument("cfl max must be greater than or equal to cfl min");
     auto ti = std::unique_ptr<rj_time_integrator>(new rj_time_integrator());
     ti->hm = hm;
-    ti->scheme = scheme;
+    ti->scheme_id = scheme;
+    ti->scheme = make_scheme(scheme);
     ti->cfl_min = cfl_min;
     ti->cfl_max = cfl_max;
     ti->recovery = cfl_recovery_strategy;
-    int n_temp = 0;
-    switch (scheme) { /* time_integrator.template.h:87-137 */
-    case RJ_SSPRK_22: n_temp = 2; ti->efficiency = 1.; break;
-    case RJ_SSPRK_33: n_temp = 2; ti->efficiency = 1.; break;
-    case RJ_ERK_11: n_temp = 1; ti->efficiency = 1.; break;
-    case RJ_ERK_22: n_temp = 2; ti->efficiency = 2.; break;
-    case RJ_ERK_33: n_temp = 3; ti->efficiency = 3.; break;
-    case RJ_ERK_43: n_temp = 4; ti->efficiency = 4.; break;
-    default: throw InvalidArgument("unknown time stepping scheme");
+    if (const char *env = std::getenv("RYUJIN_B200_STEPPING")) {
+      const std::string v(env);
+      ti->stepping = v == "host" ? STEPPING_HOST : v == "device" ? STEPPING_DEVICE : v == "graph" ? STEPPING_GRAPH : ti->stepping;
     }
-    for (int i = 0; i < n_temp; ++i) {
+    RJ_CUDA(cudaSetDevice(hm->device));
+    RJ_CUDA(cudaMalloc(&ti->d_cycle, sizeof(CycleScalars)));
+    RJ_CUDA(cudaMemset(ti->d_cycle, 0, sizeof(CycleScalars)));
+    RJ_CUDA(cudaMallocHost(&ti->h_cycle, 2 * sizeof(CycleScalars)));
+    std::memset(ti->h_cycle, 0, 2 * sizeof(CycleScalars));
+    for (int i = 0; i < ti->scheme.n_temp; ++i) {
       rj_state *s = nullptr;
       const int rc = rj_state_create(&s, hm);
       if (rc != RJ_OK)
@@ -1461,7 +1646,30 @@ int rj_time_integrator_step(rj_time_integrator *ti, rj_state *state, double t, d
   });
 }
 
-double rj_time_integrator_efficiency(const rj_time_integrator *ti) { return ti->efficiency; }
+double rj_time_integrator_efficiency(const rj_time_integrator *ti) { return ti->scheme.efficiency; }
+
+int rj_time_integrator_set_stepping(rj_time_integrator *ti, int stepping)
+{
+  return guarded([&] {
+    if (!ti || stepping < STEPPING_HOST || stepping > STEPPING_GRAPH)
+      throw InvalidArgument("rj_time_integrator_set_stepping: invalid argument");
+    ti->stepping = stepping;
+    return RJ_OK;
+  });
+}
+
+int rj_time_integrator_stepping(const rj_time_integrator *ti) { return ti->stepping; }
+
+int rj_time_integrator_graph_stats(const rj_time_integrator *ti, uint64_t stats[2])
+{
+  return guarded([&] {
+    if (!ti || !stats)
+      throw InvalidArgument("null argument");
+    stats[0] = ti->graph_captures;
+    stats[1] = ti->graph_replays;
+    return RJ_OK;
+  });
+}
 
 /* ---- host-only entry points: mesh generator, layout decoding ---- */
 

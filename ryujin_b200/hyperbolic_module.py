@@ -38,6 +38,15 @@ class CFLRecoveryStrategy(enum.IntEnum):
     bang_bang_control = 1
 
 
+class Stepping(enum.IntEnum):
+    """how TimeIntegrator drives a cycle (bit-identical results): host round trip per substep,
+    device-resident cycle, or CUDA graph replay of the device-resident cycle"""
+
+    host = 0
+    device = 1
+    graph = 2
+
+
 class InitialState(enum.IntEnum):
     uniform = 0
     contrast = 1
@@ -341,6 +350,20 @@ class TimeIntegrator:
     @property
     def efficiency(self):
         return lib.rj_time_integrator_efficiency(self._h)
+
+    @property
+    def stepping(self):
+        return Stepping(lib.rj_time_integrator_stepping(self._h))
+
+    @stepping.setter
+    def stepping(self, value):
+        check(lib.rj_time_integrator_set_stepping(self._h, int(value)))
+
+    def graph_stats(self):
+        """(graphs captured, graph launches)"""
+        st = (C.c_uint64 * 2)()
+        check(lib.rj_time_integrator_graph_stats(self._h, st))
+        return int(st[0]), int(st[1])
 
     def __del__(self):
         h = getattr(self, "_h", None)

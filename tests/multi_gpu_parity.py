@@ -26,7 +26,7 @@ import ryujin_b200 as rj  # noqa: E402
 from helpers import CASES, SW_CASES, make_mesh, make_sw_product, rel_linf, sw_bathymetry  # noqa: E402
 
 
-def run(case, n_cells, cycles, rank, world, comm, device, **ti_kw):
+def run(case, n_cells, cycles, rank, world, comm, device, stepping=None, **ti_kw):
     if case in SW_CASES:
         # shallow water with a bathymetry: also exercises the ghost exchange of initial_precomputed
         od, module = make_sw_product(case, n_cells, device=device, comm=comm, rank=rank, n_ranks=world)
@@ -39,6 +39,8 @@ def run(case, n_cells, cycles, rank, world, comm, device, **ti_kw):
         od = rj.OfflineData.from_mesh(mesh, rank=rank, n_ranks=world, device=device)
         module = rj.HyperbolicModule(od, rj.HyperbolicSystem(), rj.InitialValues(kind, **iv), comm=comm)
     ti = rj.TimeIntegrator(module, rj.TimeSteppingScheme.erk_33, **ti_kw)
+    if stepping is not None:
+        ti.stepping = stepping
     state = module.state_vector()
     state.interpolate(0.0)
     t, taus = 0.0, []
@@ -65,6 +67,15 @@ def main():
         ("sw_vortex2d", [32, 16 * world], 10, dict(cfl_min=0.25, cfl_max=0.25, cfl_recovery_strategy=rj.CFLRecoveryStrategy.none), 2e-10),
     ):
         od, module, U, taus = run(case, n_cells, cycles, rank, world, comm, local, **kw)
+        # the three ways of driving a cycle (host round trips / device-resident / CUDA graph with
+        # the NCCL exchanges captured) must agree bitwise on every rank
+        for mode in (rj.Stepping.host, rj.Stepping.graph):
+            _, _, U_m, taus_m = run(case, n_cells, cycles, rank, world, comm, local, stepping=mode, **kw)
+            same_bits = torch.tensor([int(np.array_equal(U_m, U) and np.array_equal(taus_m, taus))], device="cuda")
+            dist.all_reduce(same_bits, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print("multi-gpu %s stepping %s bit-identical to device stepping: %s" % (case, mode.name, bool(same_bits.item())), flush=True)
+            ok = ok and bool(same_bits.item())
         n_global = od.host.n_global_dofs
         k = module.k
         # gather (global index, U) on rank 0

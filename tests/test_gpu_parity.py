@@ -445,3 +445,37 @@ def test_conservation_and_symmetry_properties():
         l = module.scratch(name)[off_diag]
         assert np.all((l >= 0.0) & (l <= 1.0))
     assert module.kernel_launches() > 0
+
+
+@pytest.mark.parametrize("scheme", ["erk 33", "ssprk 33", "erk 43"])
+def test_stepping_modes_are_bit_identical(scheme):
+    """TimeIntegrator: reference control flow (host round trip per substep), device-resident
+    cycle and CUDA-graph replay must give the same bits: state, tau sequence, restart and
+    warning counters (bang-bang recovery included, cfl_max is deliberately too large)."""
+    import ryujin_b200 as rj
+
+    results = {}
+    for mode in (rj.Stepping.host, rj.Stepping.device, rj.Stepping.graph):
+        od, module = make_product("sod2d", [48, 12])
+        ti = rj.TimeIntegrator(module, _scheme(scheme), 0.3, 2.5, rj.CFLRecoveryStrategy.bang_bang_control)
+        ti.stepping = mode
+        assert ti.stepping == mode
+        state = module.state_vector()
+        state.interpolate(0.0)
+        t, taus = 0.0, []
+        for _ in range(24):
+            if t >= 0.05:
+                break
+            tau = ti.step(state, t, t_final=0.05)
+            taus.append(tau)
+            t += tau
+        results[mode] = (state.download(), np.array(taus), module.n_restarts(), module.n_warnings(), ti.graph_stats())
+    U0, taus0, nr0, nw0, _ = results[rj.Stepping.host]
+    assert nr0 > 0
+    for mode in (rj.Stepping.device, rj.Stepping.graph):
+        U, taus, nr, nw, gs = results[mode]
+        assert np.array_equal(U, U0), mode
+        assert np.array_equal(taus, taus0), mode
+        assert (nr, nw) == (nr0, nw0), mode
+    captured, replayed = results[rj.Stepping.graph][4]
+    assert replayed >= len(taus0) and 1 <= captured <= 8
