@@ -65,7 +65,8 @@ enum rj_time_stepping_scheme {
   RJ_ERK_11 = 2,
   RJ_ERK_22 = 3,
   RJ_ERK_33 = 4,
-  RJ_ERK_43 = 5
+  RJ_ERK_43 = 5,
+  RJ_ERK_54 = 6
 };
 
 /* CFLRecoveryStrategy, source/time_integrator.h */

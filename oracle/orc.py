@@ -87,7 +87,7 @@ DO_NOTHING, PERIODIC, SLIP, NO_SLIP, DIRICHLET, DYNAMIC, DIRICHLET_MOMENTUM = ra
 # initial state kinds
 UNIFORM, CONTRAST, ISENTROPIC_VORTEX = 0, 1, 2
 
-SCHEMES = {"ssprk 22": 0, "ssprk 33": 1, "erk 11": 2, "erk 22": 3, "erk 33": 4, "erk 43": 5}
+SCHEMES = {"ssprk 22": 0, "ssprk 33": 1, "erk 11": 2, "erk 22": 3, "erk 33": 4, "erk 43": 5, "erk 54": 6}
 
 SCRATCH = {"alpha": 0, "dij": 1, "lij": 2, "lij_next": 3, "pij": 4, "r": 5, "bounds": 6}
 

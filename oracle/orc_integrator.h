@@ -16,7 +16,7 @@
 
 namespace orc
 {
-  enum class TimeSteppingScheme { ssprk_22, ssprk_33, erk_11, erk_22, erk_33, erk_43 };
+  enum class TimeSteppingScheme { ssprk_22, ssprk_33, erk_11, erk_22, erk_33, erk_43, erk_54 };
   enum class CFLRecoveryStrategy { none, bang_bang_control };
 
   template <typename Desc, int dim>
@@ -46,6 +46,7 @@ namespace orc
       case TimeSteppingScheme::erk_22: n_temp = 2; efficiency_ = 2.; break;
       case TimeSteppingScheme::erk_33: n_temp = 3; efficiency_ = 3.; break;
       case TimeSteppingScheme::erk_43: n_temp = 4; efficiency_ = 4.; break;
+      case TimeSteppingScheme::erk_54: n_temp = 5; efficiency_ = 5.; break;
       }
       temp_.resize(n_temp);
       for (auto &it : temp_)
@@ -69,6 +70,7 @@ namespace orc
         case TimeSteppingScheme::erk_22: return step_erk_22(sv, t, tau_max);
         case TimeSteppingScheme::erk_33: return step_erk_33(sv, t, tau_max);
         case TimeSteppingScheme::erk_43: return step_erk_43(sv, t, tau_max);
+        case TimeSteppingScheme::erk_54: return step_erk_54(sv, t, tau_max);
         }
         return 0.;
       };
@@ -168,6 +170,47 @@ namespace orc
                    tau);
       sv.swap(temp_[3]);
       return 4. * tau;
+    }
+
+    /* time_integrator.template.h:446-510 */
+    double step_erk_54(StateVector &sv, double t, double tau_max)
+    {
+      constexpr double c = 0.2;
+      constexpr double a_21 = +0.2;
+      constexpr double a_31 = +0.26075582269554909;
+      constexpr double a_32 = +0.13924417730445096;
+      constexpr double a_41 = -0.25856517872570289;
+      constexpr double a_42 = +0.91136274166280729;
+      constexpr double a_43 = -0.05279756293710430;
+      constexpr double a_51 = +0.21623276431503774;
+      constexpr double a_52 = +0.51534223099602405;
+      constexpr double a_53 = -0.81662794199265554;
+      constexpr double a_54 = +0.88505294668159373;
+      constexpr double a_61 = -0.10511678454691901;
+      constexpr double a_62 = +0.87880047152100838;
+      constexpr double a_63 = -0.58903404061484477;
+      constexpr double a_64 = +0.46213380485434047;
+
+      module_.prepare_state_vector(sv, t);
+      const double tau = module_.step(sv, {}, {}, temp_[0], 0., tau_max / 5.);
+      module_.prepare_state_vector(temp_[0], t + 1.0 * tau);
+      module_.step(temp_[0], {&sv}, {(a_31 - a_21) / c}, temp_[1], tau);
+      module_.prepare_state_vector(temp_[1], t + 2.0 * tau);
+      module_.step(temp_[1], {&sv, &temp_[0]}, {(a_41 - a_31) / c, (a_42 - a_32) / c}, temp_[2], tau);
+      module_.prepare_state_vector(temp_[2], t + 3.0 * tau);
+      module_.step(temp_[2],
+                   {&sv, &temp_[0], &temp_[1]},
+                   {(a_51 - a_41) / c, (a_52 - a_42) / c, (a_53 - a_43) / c},
+                   temp_[3],
+                   tau);
+      module_.prepare_state_vector(temp_[3], t + 4.0 * tau);
+      module_.step(temp_[3],
+                   {&sv, &temp_[0], &temp_[1], &temp_[2]},
+                   {(a_61 - a_51) / c, (a_62 - a_52) / c, (a_63 - a_53) / c, (a_64 - a_54) / c},
+                   temp_[4],
+                   tau);
+      sv.swap(temp_[4]);
+      return 5. * tau;
     }
 
     const Module &module_;

@@ -63,6 +63,15 @@
 #ifndef RJ_MB_LOW
 #define RJ_MB_LOW 4
 #endif
+#ifndef RJ_SPLIT_LOW
+#define RJ_SPLIT_LOW 0 /* 1: run step 4 as two lighter kernels (parts 1 + 2 of k_low_order) */
+#endif
+#ifndef RJ_MB_LOW_A
+#define RJ_MB_LOW_A 6
+#endif
+#ifndef RJ_MB_LOW_B
+#define RJ_MB_LOW_B 5
+#endif
 #ifndef RJ_MB_LOW_SW
 #define RJ_MB_LOW_SW 2 /* shallow water: star states + sources need ~200 registers */
 #endif
@@ -524,8 +533,11 @@ namespace rjb
    * Step 4: low-order update, limiter bounds, r_i and P_ij,
    * hyperbolic_module.template.h:597-884.
    * ---------------------------------------------------------------------- */
-  template <class Eq, int stages>
-  __global__ void __launch_bounds__(128, Eq::shallow_water ? RJ_MB_LOW_SW : RJ_MB_LOW) k_low_order(StencilView v,
+  /* part 0: everything in one sweep.  parts 1 + 2: the same sweep as two lighter kernels,
+   * 1 = low-order update + limiter bounds (no stage states, no alpha), 2 = r_i and P_ij; each
+   * output keeps its accumulation order, the unused half is dead code for the compiler. */
+  template <class Eq, int stages, int part>
+  __global__ void __launch_bounds__(128, Eq::shallow_water ? RJ_MB_LOW_SW : (part == 0 ? RJ_MB_LOW : part == 1 ? RJ_MB_LOW_A : RJ_MB_LOW_B)) k_low_order(StencilView v,
                                                      typename Eq::Params prm,
                                                      uint32_t row_begin,
                                                      uint32_t row_end,
@@ -763,18 +775,22 @@ namespace rjb
         }
       }
 
+      if constexpr (part != 1) {
 #pragma unroll
-      for (int q = 0; q < k; ++q)
-        pij[size_t(q) * v.E_owned + e] = P_ij[q];
+        for (int q = 0; q < k; ++q)
+          pij[size_t(q) * v.E_owned + e] = P_ij[q];
+      }
     }
 
-    store_state<k>(U_new, v.ld, i, U_i_new);
-    store_state<k>(r_vec, v.ld, i, F_iH);
-
-    const double hd_i = m_i * v.measure_of_omega_inverse;
-    double b[nb];
-    limiter.bounds(prm, hd_i, b);
-    store_state<nb>(bounds, v.ld, i, b);
+    if constexpr (part != 1)
+      store_state<k>(r_vec, v.ld, i, F_iH);
+    if constexpr (part != 2) {
+      store_state<k>(U_new, v.ld, i, U_i_new);
+      const double hd_i = m_i * v.measure_of_omega_inverse;
+      double b[nb];
+      limiter.bounds(prm, hd_i, b);
+      store_state<nb>(bounds, v.ld, i, b);
+    }
   }
 
 

@@ -530,24 +530,33 @@ namespace rjb
         st.aux[s] = stage_states[s]->aux;
         st.weight[s] = stage_weights[s];
       }
-      launch_rows(k_low_order<Eq, stages>,
-                  0,
-                  od->n_owned,
-                  view(),
-                  prm,
-                  0u,
-                  od->n_owned,
-                  old_state.U,
-                  old_state.prec,
-                  old_state.aux,
-                  st,
-                  alpha,
-                  dij,
-                  scalars,
-                  new_state.U,
-                  r,
-                  bounds,
-                  pij);
+      auto run = [&](auto kernel, auto pointers) {
+        launch_rows(kernel,
+                    0,
+                    od->n_owned,
+                    view(),
+                    prm,
+                    0u,
+                    od->n_owned,
+                    old_state.U,
+                    old_state.prec,
+                    old_state.aux,
+                    pointers,
+                    alpha,
+                    dij,
+                    scalars,
+                    new_state.U,
+                    r,
+                    bounds,
+                    pij);
+      };
+#if RJ_SPLIT_LOW
+      if constexpr (!Eq::shallow_water) {
+        run(k_low_order<Eq, 0, 1>, StagePointers<0>{});
+        run(k_low_order<Eq, stages, 2>, st);
+      } else
+#endif
+        run(k_low_order<Eq, stages, 0>, st);
     }
 
     /* hyperbolic_module.template.h:236-1211 */
@@ -732,6 +741,30 @@ namespace rjb
                    next_step(3, 4, {1, 2}, {5. / 3., -10. / 3.})};
       s.result_slot = 4; s.n_temp = 4; s.tau_multiplier = 4.; s.efficiency = 4.;
       break;
+    case RJ_ERK_54: { /* time_integrator.template.h:446-510 */
+      constexpr double c = 0.2;
+      constexpr double a_21 = +0.2;
+      constexpr double a_31 = +0.26075582269554909;
+      constexpr double a_32 = +0.13924417730445096;
+      constexpr double a_41 = -0.25856517872570289;
+      constexpr double a_42 = +0.91136274166280729;
+      constexpr double a_43 = -0.05279756293710430;
+      constexpr double a_51 = +0.21623276431503774;
+      constexpr double a_52 = +0.51534223099602405;
+      constexpr double a_53 = -0.81662794199265554;
+      constexpr double a_54 = +0.88505294668159373;
+      constexpr double a_61 = -0.10511678454691901;
+      constexpr double a_62 = +0.87880047152100838;
+      constexpr double a_63 = -0.58903404061484477;
+      constexpr double a_64 = +0.46213380485434047;
+      s.program = {prepare(0, 0.), first_step(0, 1, 5.),
+                   prepare(1, 1.0), next_step(1, 2, {0}, {(a_31 - a_21) / c}),
+                   prepare(2, 2.0), next_step(2, 3, {0, 1}, {(a_41 - a_31) / c, (a_42 - a_32) / c}),
+                   prepare(3, 3.0), next_step(3, 4, {0, 1, 2}, {(a_51 - a_41) / c, (a_52 - a_42) / c, (a_53 - a_43) / c}),
+                   prepare(4, 4.0),
+                   next_step(4, 5, {0, 1, 2, 3}, {(a_61 - a_51) / c, (a_62 - a_52) / c, (a_63 - a_53) / c, (a_64 - a_54) / c})};
+      s.result_slot = 5; s.n_temp = 5; s.tau_multiplier = 5.; s.efficiency = 5.;
+    } break;
     default: throw InvalidArgument("unknown time stepping scheme");
     }
     return s;

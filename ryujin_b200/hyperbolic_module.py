@@ -31,6 +31,7 @@ class TimeSteppingScheme(enum.IntEnum):
     erk_22 = 3
     erk_33 = 4
     erk_43 = 5
+    erk_54 = 6
 
 
 class CFLRecoveryStrategy(enum.IntEnum):

@@ -241,3 +241,34 @@ def sw_riemann():
 sw = sw_riemann()
 if sw:
     dump("shallow_water_riemann_solver.json", sw)
+
+
+# --------------------------------------------------------------------------
+def prm_runs():
+    """Parameter files of the reference's end-to-end verification tests together with the
+    numbers of their golden outputs (input decks are test data, not source): what
+    `python -m ryujin_b200 <file.prm>` must reproduce.  tests/test_prm_frontend.py"""
+    runs = []
+    for sub, stem in [
+        ("euler", "verification-isentropic_vortex-2d-erk33-l5"),
+        ("euler", "verification-isentropic_vortex-2d-erk33-l6"),
+        ("euler", "verification-isentropic_vortex-2d-ssprk33-l5"),
+        ("euler", "verification-isentropic_vortex-2d-ssprk33-l6"),
+        ("shallow_water", "verification-smooth_vortex-erk33-l6"),
+        ("shallow_water", "verification-ritter_dam_break-erk33-l7"),
+    ]:
+        out = read("tests/%s/%s.output" % (sub, stem))
+        vals = {}
+        for key, tag in [("dofs", "#dofs"), ("t", "t "), ("Linf", "Linf"), ("L1", "L1"), ("L2", "L2")]:
+            m = re.search(r"^%s\s*=\s*(\S+)" % re.escape(tag.strip()), out, re.M)
+            vals[key] = float(m.group(1))
+        runs.append({
+            "name": "%s/%s" % (sub, stem),
+            "prm": read("tests/%s/%s.prm" % (sub, stem)),
+            "output": out,
+            "expected": vals,
+        })
+    return {"source": "tests/{euler,shallow_water}/verification-*.{prm,output}", "runs": runs}
+
+
+dump("prm_runs.json", prm_runs())

@@ -145,7 +145,8 @@ def _scheme(name):
 
     return {"erk 33": rj.TimeSteppingScheme.erk_33, "ssprk 33": rj.TimeSteppingScheme.ssprk_33,
             "erk 11": rj.TimeSteppingScheme.erk_11, "erk 22": rj.TimeSteppingScheme.erk_22,
-            "erk 43": rj.TimeSteppingScheme.erk_43, "ssprk 22": rj.TimeSteppingScheme.ssprk_22}[name]
+            "erk 43": rj.TimeSteppingScheme.erk_43, "ssprk 22": rj.TimeSteppingScheme.ssprk_22,
+            "erk 54": rj.TimeSteppingScheme.erk_54}[name]
 
 
 def run_cycles(module, sims, n_cycles, scheme_name, cfl_min=0.45, cfl_max=0.9, recovery="bang bang control"):
@@ -243,7 +244,7 @@ def test_config1_sod_2d_256x256_100_cycles(oracle, oracle_vcl):
     assert (module.n_restarts(), module.n_warnings()) == sims[0].counters()
 
 
-@pytest.mark.parametrize("scheme", ["ssprk 22", "ssprk 33", "erk 11", "erk 22", "erk 43"])
+@pytest.mark.parametrize("scheme", ["ssprk 22", "ssprk 33", "erk 11", "erk 22", "erk 43", "erk 54"])
 def test_other_schemes(oracle, oracle_vcl, scheme):
     od, module = make_product("sod2d", [64, 16])
     sims = both(oracle, oracle_vcl, "sod2d", od.host)
@@ -447,7 +448,7 @@ def test_conservation_and_symmetry_properties():
     assert module.kernel_launches() > 0
 
 
-@pytest.mark.parametrize("scheme", ["erk 33", "ssprk 33", "erk 43"])
+@pytest.mark.parametrize("scheme", ["erk 33", "ssprk 33", "erk 54"])
 def test_stepping_modes_are_bit_identical(scheme):
     """TimeIntegrator: reference control flow (host round trip per substep), device-resident
     cycle and CUDA-graph replay must give the same bits: state, tau sequence, restart and

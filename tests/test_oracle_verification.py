@@ -39,3 +39,27 @@ def test_isentropic_vortex_verification(oracle, scheme, key, refinement):
     for name in ("Linf", "L1", "L2"):
         assert abs(err[name] - ref[name]) <= (1e-10 if refinement == 7 else 1e-11) * ref[name], (name, err[name], ref[name])
     assert sim.counters() == (0, 0)
+
+
+def test_erk54_is_consistent_with_erk33(oracle):
+    """erk 54 (time_integrator.template.h:446-510) has no Euler golden in the reference; pin the
+    restated coefficients through consistency: same vortex, same cfl per substep -> 5/3 fewer
+    cycles to the same final time, and error norms within 1 % of erk 33's."""
+    from oracle import orc
+
+    res = {}
+    for scheme in ("erk 33", "erk 54"):
+        n = 32
+        off = oracle.assemble([n, n], [-5.0, -5.0], [10.0 / n, 10.0 / n], [orc.DIRICHLET] * 4)
+        sim = off.euler_sim(kind=orc.ISENTROPIC_VORTEX, direction=(1.0, 1.0), position=(-1.0, -1.0), mach=1.0, beta=5.0)
+        sim.configure_time_integrator(scheme, 0.2, 0.2, "none")
+        sim.interpolate(0.0)
+        t, cycles = 0.0, 0
+        while t < 1.0:
+            t += sim.time_step(t)
+            cycles += 1
+        res[scheme] = (cycles, t, sim.errors(t))
+    assert res["erk 33"][0] == 45 and res["erk 54"][0] == 27
+    assert abs(res["erk 33"][1] - res["erk 54"][1]) < 1e-8
+    for k in ("Linf", "L1", "L2"):
+        assert abs(res["erk 54"][2][k] / res["erk 33"][2][k] - 1.0) < 1e-2
