@@ -237,7 +237,8 @@ namespace rjb
   template <class Eq>
   __global__ void k_precompute(StencilView v,
                                typename Eq::Params prm,
-                               uint32_t n_relevant,
+                               uint32_t row_begin,
+                               uint32_t row_end,
                                const double *__restrict__ U,
                                const double *__restrict__ initial_precomputed,
                                double *__restrict__ prec,
@@ -247,8 +248,8 @@ namespace rjb
      * exchanged ghost state (bit-identical to the owner's values), which replaces
      * the ghost exchange of the precomputed vector (C2, :157-160) */
     constexpr int k = Eq::k, np = Eq::n_prec, na = Eq::n_aux;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_relevant)
+    const uint32_t i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row_end)
       return;
     if (i < v.n_owned && v.row_length[i] <= 1)
       return;

@@ -82,6 +82,14 @@ struct rj_hyperbolic_module {
   rj_comm *comm = nullptr;
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
+  /* Halo exchanges run on a second stream so that they overlap with the interior rows of the
+   * kernel that produced the data (the reference's SynchronizationDispatch, openmp.h:141-182:
+   * "fire the exchange once the export rows are done").  `cur` is the stream launch() and the
+   * exchanges currently target. */
+  cudaStream_t comm_stream = nullptr;
+  cudaStream_t cur = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = true;
 
   rj_equation_desc eq{};
   rj_module_params mp{};
@@ -219,13 +227,13 @@ struct rj_hyperbolic_module {
         RJ_CUDA(cudaEventCreate(&prof_events[prof_used]));
         RJ_CUDA(cudaEventCreate(&prof_events[prof_used + 1]));
       }
-      RJ_CUDA(cudaEventRecord(prof_events[prof_used], stream));
-      kernel<<<grid, block, 0, stream>>>(args...);
-      RJ_CUDA(cudaEventRecord(prof_events[prof_used + 1], stream));
+      RJ_CUDA(cudaEventRecord(prof_events[prof_used], cur));
+      kernel<<<grid, block, 0, cur>>>(args...);
+      RJ_CUDA(cudaEventRecord(prof_events[prof_used + 1], cur));
       prof_slots.push_back(prof_slot);
       prof_used += 2;
     } else
-      kernel<<<grid, block, 0, stream>>>(args...);
+      kernel<<<grid, block, 0, cur>>>(args...);
     RJ_CUDA(cudaGetLastError());
     ++launches;
   }
@@ -254,6 +262,27 @@ struct rj_hyperbolic_module {
   uint64_t prof_count[P_N_SLOTS] = {};
 
   void tag(int slot) { prof_slot = slot; }
+
+  /* -------- two-stream overlap -------- */
+  bool overlapping() const { return overlap && comm && comm->n_ranks > 1 && !od->neighbors.empty() && comm_stream; }
+  /* rows [0, n_export_rows()) have ghost columns and are ghosts elsewhere; slice aligned */
+  uint32_t n_export_rows() const { return std::min<uint32_t>(od->n_owned, (od->n_export + 31u) & ~31u); }
+  /* what follows on the communication stream starts after everything enqueued on the main stream */
+  void fork_comm()
+  {
+    RJ_CUDA(cudaEventRecord(ev_fork, stream));
+    RJ_CUDA(cudaStreamWaitEvent(comm_stream, ev_fork, 0));
+    cur = comm_stream;
+  }
+  /* back to the main stream without waiting for the communication stream */
+  void continue_main() { cur = stream; }
+  /* the main stream waits for everything enqueued on the communication stream */
+  void join_comm()
+  {
+    RJ_CUDA(cudaEventRecord(ev_join, comm_stream));
+    RJ_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+    cur = stream;
+  }
 
   /* call after a stream synchronize */
   void collect_profile()
@@ -295,14 +324,14 @@ struct rj_hyperbolic_module {
                            ncclDouble,
                            nb.rank,
                            comm->comm,
-                           stream));
+                           cur));
         if (nb.ghost_count)
           RJ_NCCL(ncclRecv(v + size_t(c) * ld + nb.ghost_start,
                            nb.ghost_count,
                            ncclDouble,
                            nb.rank,
                            comm->comm,
-                           stream));
+                           cur));
       }
     }
     RJ_NCCL(ncclGroupEnd());
@@ -328,10 +357,10 @@ struct rj_hyperbolic_module {
                          ncclDouble,
                          nb.rank,
                          comm->comm,
-                         stream));
+                         cur));
       if (nb.mat_recv_count)
         RJ_NCCL(ncclRecv(
-            m + nb.mat_recv_offset, nb.mat_recv_count, ncclDouble, nb.rank, comm->comm, stream));
+            m + nb.mat_recv_offset, nb.mat_recv_count, ncclDouble, nb.rank, comm->comm, cur));
     }
     RJ_NCCL(ncclGroupEnd());
   }
@@ -374,6 +403,12 @@ rj_hyperbolic_module::~rj_hyperbolic_module()
     cudaEventDestroy(ev);
   if (h_scalars)
     cudaFreeHost(h_scalars);
+  if (ev_fork)
+    cudaEventDestroy(ev_fork);
+  if (ev_join)
+    cudaEventDestroy(ev_join);
+  if (comm_stream)
+    cudaStreamDestroy(comm_stream);
   if (owns_stream && stream)
     cudaStreamDestroy(stream);
 }
@@ -493,6 +528,7 @@ namespace rjb
     {
       RJ_CUDA(cudaSetDevice(od->device));
       const StencilView v = view();
+      cur = stream;
       tag(P_BC);
       launch(k_apply_boundary_conditions<Eq, InitialValuesDevice>,
              od->n_bgroups,
@@ -510,15 +546,33 @@ namespace rjb
              cycle,
              tau_factor,
              state.U);
-      tag(P_OTHER);
-      exchange_vector(state.U, Eq::k); /* C1 */
-      /* precomputed values for owned AND ghost rows from the exchanged state: replaces C2 */
-      tag(P_PRECOMPUTE);
-      launch(k_precompute<Eq>, od->n_relevant, 256, v, prm, od->n_relevant, state.U, initial_precomputed, state.prec, state.aux);
+      /* C1, then precomputed values for owned AND ghost rows from the exchanged state (replaces
+       * C2).  With neighbours: the exchange and the ghost rows run on the communication stream
+       * while the owned rows are precomputed on the main stream. */
+      auto precompute = [&](uint32_t begin, uint32_t end) {
+        tag(P_PRECOMPUTE);
+        if (end > begin)
+          launch(k_precompute<Eq>, end - begin, 256, v, prm, begin, end, state.U, initial_precomputed, state.prec, state.aux);
+      };
+      if (overlapping()) {
+        fork_comm();
+        tag(P_OTHER);
+        exchange_vector(state.U, Eq::k);
+        precompute(od->n_owned, od->n_relevant);
+        continue_main();
+        precompute(0, od->n_owned);
+        join_comm();
+      } else {
+        tag(P_OTHER);
+        exchange_vector(state.U, Eq::k);
+        precompute(0, od->n_relevant);
+      }
     }
 
     template <int stages>
-    void low_order(const rj_state &old_state,
+    void low_order(uint32_t begin,
+                   uint32_t end,
+                   const rj_state &old_state,
                    const rj_state *const *stage_states,
                    const double *stage_weights,
                    rj_state &new_state)
@@ -532,12 +586,12 @@ namespace rjb
       }
       auto run = [&](auto kernel, auto pointers) {
         launch_rows(kernel,
-                    0,
-                    od->n_owned,
+                    begin,
+                    end,
                     view(),
                     prm,
-                    0u,
-                    od->n_owned,
+                    begin,
+                    end,
                     old_state.U,
                     old_state.prec,
                     old_state.aux,
@@ -559,7 +613,11 @@ namespace rjb
         run(k_low_order<Eq, stages, 0>, st);
     }
 
-    /* hyperbolic_module.template.h:236-1211 */
+    /* hyperbolic_module.template.h:236-1211.
+     *
+     * With neighbours every sweep whose result is exchanged runs in two launches: rows
+     * [0, nx) (the export rows; only they read ghost columns) first, then the exchange on the
+     * communication stream concurrently with rows [nx, n_owned) on the main stream. */
     void enqueue_step(const rj_state &old_state,
                       int stages,
                       const rj_state *const *stage_states,
@@ -576,6 +634,28 @@ namespace rjb
         throw InvalidArgument("rj_hyperbolic_module_step: old and new state must differ");
       const StencilView v = view();
       const uint32_t n_owned = od->n_owned;
+      cur = stream;
+      const bool ov = overlapping();
+      const bool multi = comm && comm->n_ranks > 1;
+      /* two row ranges per sweep when overlapping, one otherwise */
+      const uint32_t nx = ov ? n_export_rows() : n_owned;
+
+      /* sweep(f): f(begin, end) on the export rows, `exchange` on the communication stream,
+       * f on the interior rows meanwhile; the main stream continues after both */
+      auto sweep = [&](auto &&f, auto &&exchange) {
+        f(0u, nx);
+        if (ov) {
+          fork_comm();
+          tag(P_OTHER);
+          exchange();
+          continue_main();
+          f(nx, n_owned);
+          join_comm();
+        } else {
+          tag(P_OTHER);
+          exchange();
+        }
+      };
 
       tag(P_OTHER);
       launch(k_reset_scalars, 1, 1, scalars);
@@ -586,82 +666,96 @@ namespace rjb
         constexpr int W = RJ_DIJ_W; /* warps per slice in the edge-parallel d_ij kernel */
         launch(k_dij<Eq, W>, size_t(od->n_slices) * 32 * W, 32 * W, v, prm, 0u, od->n_slices, old_state.U, old_state.prec, dij);
       }
-      tag(P_ALPHA);
-      launch_rows(k_alpha<Eq>, 0, n_owned, v, prm, 0u, n_owned, old_state.U, old_state.prec, old_state.aux, alpha);
-      tag(P_OTHER);
-      exchange_vector(alpha, 1);
+      sweep(
+          [&](uint32_t b, uint32_t e) {
+            tag(P_ALPHA);
+            launch_rows(k_alpha<Eq>, b, e, v, prm, b, e, old_state.U, old_state.prec, old_state.aux, alpha);
+            if (e == n_owned && (b < e || b == 0)) {
+              /* Step 3: boundary d_ij, d_ii, tau_max (need d_ij only) */
+              tag(P_BOUNDARY_DIJ);
+              launch(k_boundary_dij<Eq>,
+                     od->n_pairs,
+                     128,
+                     od->n_pairs,
+                     od->pair_i,
+                     od->pair_j,
+                     od->pair_e,
+                     od->pair_eT,
+                     od->pair_cji,
+                     od->ld,
+                     od->E_owned,
+                     prm,
+                     old_state.U,
+                     old_state.prec,
+                     dij);
+              tag(P_DII_TAU);
+              launch_rows(k_dii_tau, 0, n_owned, v, 0u, n_owned, cfl, dij, scalars);
+              tag(P_OTHER);
+              launch(k_tau_local, 1, 1, scalars, tau_source, (const CycleScalars *)cycle);
+            }
+          },
+          [&] { exchange_vector(alpha, 1); });
 
-      /* Step 3: boundary d_ij, d_ii, tau_max; C4 */
-      tag(P_BOUNDARY_DIJ);
-      launch(k_boundary_dij<Eq>,
-             od->n_pairs,
-             128,
-             od->n_pairs,
-             od->pair_i,
-             od->pair_j,
-             od->pair_e,
-             od->pair_eT,
-             od->pair_cji,
-             od->ld,
-             od->E_owned,
-             prm,
-             old_state.U,
-             old_state.prec,
-             dij);
-      tag(P_DII_TAU);
-      launch_rows(k_dii_tau, 0, n_owned, v, 0u, n_owned, cfl, dij, scalars);
-      tag(P_OTHER);
-      launch(k_tau_local, 1, 1, scalars, tau_source, (const CycleScalars *)cycle);
-      if (comm && comm->n_ranks > 1)
-        RJ_NCCL(ncclAllReduce(
-            &scalars->tau_max, &scalars->tau_max, 1, ncclDouble, ncclMin, comm->comm, stream));
+      /* C4: all NCCL traffic of this communicator is issued on one stream */
+      if (multi) {
+        if (ov)
+          fork_comm();
+        RJ_NCCL(ncclAllReduce(&scalars->tau_max, &scalars->tau_max, 1, ncclDouble, ncclMin, comm->comm, cur));
+        if (ov)
+          join_comm();
+      }
       launch(k_tau_finalize, 1, 1, scalars, tau_source, cycle);
 
       /* Step 4: low-order update, bounds, r_i, P_ij; C6 */
-      tag(P_LOW_ORDER);
-      switch (stages) {
-      case 0: low_order<0>(old_state, stage_states, stage_weights, new_state); break;
-      case 1: low_order<1>(old_state, stage_states, stage_weights, new_state); break;
-      case 2: low_order<2>(old_state, stage_states, stage_weights, new_state); break;
-      case 3: low_order<3>(old_state, stage_states, stage_weights, new_state); break;
-      case 4: low_order<4>(old_state, stage_states, stage_weights, new_state); break;
-      }
-      tag(P_OTHER);
-      exchange_vector(r, Eq::k);
+      sweep(
+          [&](uint32_t b, uint32_t e) {
+            tag(P_LOW_ORDER);
+            switch (stages) {
+            case 0: low_order<0>(b, e, old_state, stage_states, stage_weights, new_state); break;
+            case 1: low_order<1>(b, e, old_state, stage_states, stage_weights, new_state); break;
+            case 2: low_order<2>(b, e, old_state, stage_states, stage_weights, new_state); break;
+            case 3: low_order<3>(b, e, old_state, stage_states, stage_weights, new_state); break;
+            case 4: low_order<4>(b, e, old_state, stage_states, stage_weights, new_state); break;
+            }
+          },
+          [&] { exchange_vector(r, Eq::k); });
 
       /* Step 5: P_ij correction and first l_ij; C7 */
       const unsigned int n_iterations = mp.limiter_iterations;
-      if (n_iterations != 0) {
-        tag(P_PIJ_LIJ);
-        launch_rows(k_pij_lij<Eq>, 0, n_owned, v, prm, 0u, n_owned, new_state.U, r, bounds, scalars, pij, lij);
-        tag(P_OTHER);
-        exchange_matrix(lij);
-      }
+      if (n_iterations != 0)
+        sweep(
+            [&](uint32_t b, uint32_t e) {
+              tag(P_PIJ_LIJ);
+              launch_rows(k_pij_lij<Eq>, b, e, v, prm, b, e, new_state.U, r, bounds, scalars, pij, lij);
+            },
+            [&] { exchange_matrix(lij); });
 
       /* Steps 6, 7; C8 */
       for (unsigned int pass = 0; pass < n_iterations; ++pass) {
         const bool last_round = (pass + 1 == n_iterations);
         if ((n_iterations == 2) && last_round)
           std::swap(lij, lij_next);
-        tag(last_round ? P_HIGH_ORDER_FINAL : P_HIGH_ORDER_NEXT);
-        if (last_round)
+        if (last_round) {
+          tag(P_HIGH_ORDER_FINAL);
           launch_rows(k_high_order<Eq, true>, 0, n_owned, v, prm, 0u, n_owned, bounds, pij, lij, lij_next, new_state.U);
-        else {
-          launch_rows(k_high_order<Eq, false>, 0, n_owned, v, prm, 0u, n_owned, bounds, pij, lij, lij_next, new_state.U);
-          tag(P_OTHER);
-          exchange_matrix(lij_next);
-        }
+        } else
+          sweep(
+              [&](uint32_t b, uint32_t e) {
+                tag(P_HIGH_ORDER_NEXT);
+                launch_rows(k_high_order<Eq, false>, b, e, v, prm, b, e, bounds, pij, lij, lij_next, new_state.U);
+              },
+              [&] { exchange_matrix(lij_next); });
       }
 
       /* C9 and the host side of :571-578,1190-1210 */
-      if (comm && comm->n_ranks > 1)
-        RJ_NCCL(ncclAllReduce(&scalars->restart_needed,
-                              &scalars->restart_needed,
-                              1,
-                              ncclInt,
-                              ncclMax,
-                              comm->comm,
-                              stream));
+      tag(P_OTHER);
+      if (multi) {
+        if (ov)
+          fork_comm();
+        RJ_NCCL(ncclAllReduce(&scalars->restart_needed, &scalars->restart_needed, 1, ncclInt, ncclMax, comm->comm, cur));
+        if (ov)
+          join_comm();
+      }
       if (cycle)
         launch(k_cycle_record, 1, 1, (const StepScalars *)scalars, cycle, substep);
     }
@@ -1257,6 +1351,17 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
       RJ_CUDA(cudaStreamCreateWithFlags(&hm->stream, cudaStreamNonBlocking));
       hm->owns_stream = true;
     }
+    hm->cur = hm->stream;
+    if (comm && comm->n_ranks > 1) {
+      /* highest priority: a ready exchange must not queue behind the blocks of the interior sweep */
+      int prio_low = 0, prio_high = 0;
+      RJ_CUDA(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+      RJ_CUDA(cudaStreamCreateWithPriority(&hm->comm_stream, cudaStreamNonBlocking, prio_high));
+      RJ_CUDA(cudaEventCreateWithFlags(&hm->ev_fork, cudaEventDisableTiming));
+      RJ_CUDA(cudaEventCreateWithFlags(&hm->ev_join, cudaEventDisableTiming));
+    }
+    if (const char *env = std::getenv("RYUJIN_B200_OVERLAP"))
+      hm->overlap = std::string(env) != "0";
 
     /* InitialValues::parse_parameters_callback: normalize direction */
     InitialValuesDevice &d = hm->iv;
