@@ -109,9 +109,30 @@ class TimeLoop:
         self.error_normalize = A.get_bool("error normalize", True)
         self.terminal_update_interval = A.get_float("terminal update interval", 5.0)
         for key in ("enable checkpointing", "enable output full", "enable output levelsets",
-                    "enable compute quantities", "enable mesh adaptivity", "resume"):
+                    "enable mesh adaptivity", "resume"):
             if A.get_bool(key, False):
                 raise NotOnThePath("A - TimeLoop/%s = true is outside the explicit hyperbolic update" % key)
+        # Quantities (source/quantities.template.h): only the space averaged time series of interior
+        # manifolds that select every node (level set "0."), the form the reference's regression
+        # decks use; the series is printed at the end like the reference's `debug filename` dump
+        self.enable_compute_quantities = A.get_bool("enable compute quantities", False)
+        self.debug_filename = A.get_str("debug filename", "")
+        self.time_series = []
+        K = p.subsection("K - Quantities")
+        manifolds = [m.strip() for m in K.get_str("interior manifolds", "").split(";") if m.strip()]
+        if K.get_str("boundary manifolds", "").strip():
+            raise NotOnThePath("K - Quantities/boundary manifolds")
+        self.manifold_name = None
+        if self.enable_compute_quantities:
+            for m in manifolds:
+                name, level_set, options = [x.strip() for x in m.split(":")]
+                try:
+                    everywhere = float(level_set) == 0.0
+                except ValueError:
+                    everywhere = False
+                if not everywhere or "space_averaged" not in options:
+                    raise NotOnThePath("K - Quantities/interior manifolds »%s«: only level set 0 with space_averaged" % m)
+                self.manifold_name = name
 
         # ---- B - Equation
         B = p.subsection("B - Equation")
@@ -272,6 +293,8 @@ class TimeLoop:
         t_start = time.perf_counter()
         last_terminal = float("inf") if self.terminal_update_interval == 0.0 else float("-inf")
         while True:
+            if self.manifold_name is not None:
+                self.time_series.append((t, self.space_averaged_primitive_state()))
             if t >= timer_cycle * self.timer_granularity:
                 timer_cycle += 1  # output / postprocessing ticks of the reference: nothing to do here
             if t >= relax * self.t_final:
@@ -293,7 +316,42 @@ class TimeLoop:
         result = dict(cycle=cycle, t=t, n_dofs=self.n_dofs, wall_time=self.wall_time)
         if self.enable_compute_error:
             result.update(self.compute_error(t))
+        if self.manifold_name is not None:
+            result["time_series"] = self.time_series
+            if self.rank == 0 and self.debug_filename.endswith("space_averaged_time_series.dat"):
+                self.print_time_series()
         return result
+
+    def primitive_state(self, U):
+        """View::to_primitive_state: (rho, v, p) / (h, v)"""
+        v = U[:, 1 : 1 + self.dim] / U[:, :1]
+        if self.equation == Equation.euler:
+            gamma = self.module.hyperbolic_system.desc.gamma
+            p = (gamma - 1.0) * (U[:, -1] - 0.5 * U[:, 0] * np.sum(v * v, axis=1))
+            return np.column_stack([U[:, 0], v, p])
+        return np.column_stack([U[:, 0], v])
+
+    def space_averaged_primitive_state(self):
+        """Quantities::internal_accumulate (quantities.template.h:369-423): lumped-mass weighted
+        average of the primitive state and of its second moments over all (unconstrained) nodes"""
+        host = self.offline_data.host
+        U = self.gather_global(self.state.download())
+        m = self.gather_global(np.asarray(host.mi[: host.n_owned], dtype=np.float64).reshape(-1, 1))[:, 0]
+        prim = self.primitive_state(U)
+        w = m / np.sum(m)
+        return np.concatenate([w @ prim, w @ (prim * prim)])
+
+    def print_time_series(self):
+        """<basename>-<manifold>-R0000-space_averaged_time_series.dat as the reference writes it"""
+        names = {Equation.euler: ["rho"] + ["v_%d" % (d + 1) for d in range(self.dim)] + ["p"],
+                 Equation.shallow_water: ["h"] + ["v_%d" % (d + 1) for d in range(self.dim)]}[self.equation]
+        if self.dim == 1:
+            names[1] = "v"
+        print("# time t\tprimitive state (%s)\t and 2nd moments" % ", ".join(names), file=self.out)
+        k = len(names)
+        for t, values in self.time_series:
+            print("%.14e\t%s\t%s" % (t, " ".join("%.14e" % x for x in values[:k]), " ".join("%.14e" % x for x in values[k:])),
+                  file=self.out)
 
     def throughput(self, cycle, wall):
         """MQ/s of print_throughput (:1156-1162): cycles * n_dofs * efficiency / wall time"""

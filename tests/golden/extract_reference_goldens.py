@@ -272,3 +272,26 @@ def prm_runs():
 
 
 dump("prm_runs.json", prm_runs())
+
+
+# --------------------------------------------------------------------------
+def mass_conservation():
+    """tests/euler/check-mass-conservation_01.{prm,output}: uniform Mach 3 state in a closed slip
+    box, ssprk 33 at cfl 0.9; the output is the space averaged primitive state (and its second
+    moments) at the start of every cycle -- a per-cycle time series through reflecting shocks."""
+    out = read("tests/euler/check-mass-conservation_01.output")
+    rows = []
+    for line in out.splitlines():
+        if line.startswith("[") or line.startswith("#") or not line.strip():
+            continue
+        rows.append(floats(line))
+    assert all(len(r) == 9 for r in rows)
+    return {
+        "source": "tests/euler/check-mass-conservation_01.{prm,output}",
+        "prm": read("tests/euler/check-mass-conservation_01.prm"),
+        "columns": ["t", "rho", "v_1", "v_2", "p", "rho^2", "v_1^2", "v_2^2", "p^2"],
+        "rows": rows,
+    }
+
+
+dump("euler_mass_conservation.json", mass_conservation())

@@ -63,3 +63,48 @@ def test_erk54_is_consistent_with_erk33(oracle):
     assert abs(res["erk 33"][1] - res["erk 54"][1]) < 1e-8
     for k in ("Linf", "L1", "L2"):
         assert abs(res["erk 54"][2][k] / res["erk 33"][2][k] - 1.0) < 1e-2
+
+
+def space_averaged_primitive(U, mi, gamma=1.4):
+    """Quantities::internal_accumulate (quantities.template.h:369-423) for the interior manifold
+    with level set 0 (every node): lumped-mass weighted average of the primitive state and of
+    its second moments"""
+    rho = U[:, 0]
+    v = U[:, 1:-1] / rho[:, None]
+    p = (gamma - 1.0) * (U[:, -1] - 0.5 * rho * np.sum(v * v, axis=1))
+    prim = np.column_stack([rho, v, p])
+    m = mi / np.sum(mi)
+    return np.concatenate([m @ prim, m @ (prim * prim)])
+
+
+def test_mass_conservation_time_series(oracle):
+    """tests/euler/check-mass-conservation_01: Mach 3 uniform state in a closed box with slip walls
+    (shocks form at the right wall and reflect), 65^2 dofs, ssprk 33 at cfl 0.9.  The golden holds
+    t and the space averaged primitive state at the start of each cycle (19 rows)."""
+    from oracle import orc
+
+    g = load_golden("euler_mass_conservation.json")
+    n = 64
+    off = oracle.assemble([n, n], [0.0, 0.0], [20.0 / n, 20.0 / n], [orc.SLIP] * 4)
+    assert off.n == 4225
+    sim = off.euler_sim(kind=orc.UNIFORM, direction=(1.0, 0.0), position=(0.0, 0.0), primitive=(1.4, 3.0, 1.0))
+    sim.configure_time_integrator("ssprk 33", 0.9, 0.9, "none")
+    sim.interpolate(0.0)
+    mi = off.arrays()["mi"]
+    t = 0.0
+    rows = []
+    while True:
+        rows.append(np.concatenate([[t], space_averaged_primitive(sim.get_U(0).reshape(-1, 4), mi)]))
+        if t >= 0.5:
+            break
+        t += sim.time_step(t)
+    ref = np.array(g["rows"])
+    got = np.array(rows)
+    assert got.shape == ref.shape == (19, 9)
+    assert np.max(np.abs(got[:, 0] - ref[:, 0])) <= 2e-14  # the tau sequence of all cycles
+    # mass is conserved to round-off in a closed box
+    assert np.max(np.abs(got[:, 1] - 1.4)) < 2e-14
+    scale = np.maximum(np.abs(ref), 1e-3)  # <v_2> is round-off noise around zero
+    err = np.abs(got - ref) / scale
+    assert np.max(err[:, [1, 2, 4, 5, 6, 8]]) < 1e-12, np.max(err, axis=0)
+    assert np.max(np.abs(got[:, 3])) < 1e-14 and np.max(err[:, 7]) < 1e-9

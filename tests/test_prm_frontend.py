@@ -154,3 +154,30 @@ def test_reference_decks_reproduce_their_golden_outputs(index):
         if line.startswith("[INFO]") or line.startswith("Normalized"):
             assert line.strip() in [l.strip() for l in text.splitlines()], line
     assert loop.unused_entries() == []
+
+
+@pytest.mark.gpu
+def test_mass_conservation_deck_reproduces_the_golden_time_series():
+    """tests/euler/check-mass-conservation_01.{prm,output} unmodified: Mach 3 flow in a closed box
+    with slip walls, ssprk 33 at cfl 0.9; the golden is the space averaged primitive state at the
+    start of every cycle (K - Quantities, interior manifold with level set 0)."""
+    import ryujin_b200 as rj
+    from ryujin_b200 import prm
+
+    g = load_golden("euler_mass_conservation.json")
+    out = io.StringIO()
+    loop = rj.TimeLoop(prm.parse(g["prm"]), out=out)
+    result = loop.run()
+    ref = np.array(g["rows"])
+    got = np.array([[t] + list(v) for t, v in result["time_series"]])
+    assert got.shape == ref.shape == (19, 9)
+    assert np.max(np.abs(got[:, 0] - ref[:, 0])) <= 1e-12
+    assert np.max(np.abs(got[:, 1] - 1.4)) < 2e-14  # mass conservation
+    scale = np.maximum(np.abs(ref), 1e-3)
+    err = np.abs(got - ref) / scale
+    assert np.max(err[:, [1, 2, 4, 5, 6, 8]]) < 1e-10, np.max(err, axis=0)
+    # and the printed dump parses back to the same numbers, in the reference's layout
+    lines = [l for l in out.getvalue().splitlines() if l and not l.startswith("[") and not l.startswith("#")]
+    assert out.getvalue().count("# time t\tprimitive state (rho, v_1, v_2, p)\t and 2nd moments") == 1
+    assert len(lines) == 19 and all(len(l.split("\t")) == 3 for l in lines)
+    assert abs(float(lines[5].split("\t")[0]) - ref[5, 0]) < 1e-13
