@@ -312,11 +312,17 @@ namespace
     void finalize()
     {
       iv.transform.normalize();
+      /* InitialValues::interpolate_initial_precomputed_vector: bathymetry of the configuration
+       * at the nodes (flat when the offline data came without a mesh) */
+      std::vector<double> z(off->od.n_owned, 0.);
+      if (off->has_mesh)
+        for (unsigned int i = 0; i < off->od.n_owned; ++i)
+          z[i] = iv.bathymetry(off->mesh.position(i));
       module.reset(new Module(
           off->od,
           sys,
           [this](const Vec<dim> &x, double t) { return iv.initial_state(x, t); },
-          std::vector<double>(off->od.n_owned, 0.) /* flat bathymetry */));
+          std::move(z)));
       module->prepare();
       ti.reset(new TimeIntegrator<Desc, dim>(*module));
       ti->prepare();

@@ -79,7 +79,7 @@ SW_PARAM_DEFAULTS = dict(
 )
 
 # shallow water initial states (same numbers as enum rj_initial_state_kind)
-SW_CIRCULAR_DAM_BREAK, SW_UNIFORM, SW_RITTER_DAM_BREAK, SW_SMOOTH_VORTEX = 16, 17, 18, 19
+SW_CIRCULAR_DAM_BREAK, SW_UNIFORM, SW_RITTER_DAM_BREAK, SW_SMOOTH_VORTEX, SW_SLOPING_FRICTION = 16, 17, 18, 19, 20
 
 # Boundary ids, source/discretization.h:48-123
 DO_NOTHING, PERIODIC, SLIP, NO_SLIP, DIRICHLET, DYNAMIC, DIRICHLET_MOMENTUM = range(7)

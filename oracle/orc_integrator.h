@@ -380,7 +380,7 @@ namespace orc
   namespace sw
   {
     /* kinds match enum rj_initial_state_kind of include/ryujin_b200.h */
-    enum class InitialStateKind { circular_dam_break = 16, uniform = 17, ritter_dam_break = 18, smooth_vortex = 19 };
+    enum class InitialStateKind { circular_dam_break = 16, uniform = 17, ritter_dam_break = 18, smooth_vortex = 19, sloping_friction = 20 };
 
     template <int dim>
     struct InitialValues {
@@ -392,7 +392,8 @@ namespace orc
       InitialTransform<dim> transform;
       /* circular dam break: (still water depth, radius, dam amplitude)
        * uniform: (h, u); ritter: (time initial, left water depth)
-       * smooth vortex: (reference depth, mach number, beta) */
+       * smooth vortex: (reference depth, mach number, beta)
+       * sloping friction: (ramp slope, initial discharge) */
       std::array<double, 4> p{{0.5, 2.5, 2.5, 0.}};
 
       explicit InitialValues(const Sys &s)
@@ -450,8 +451,28 @@ namespace orc
             s[2] = h * v;
           return s;
         }
+        case InitialStateKind::sloping_friction: {
+          /* initial_state_sloping_friction.h:54-69: steady flow down an inclined plane with
+           * Manning friction */
+          const double n = sys.prm.manning_friction_coefficient;
+          const double slope = p[0], q_0 = p[1];
+          const double exponent = 1. / (2. + 4. / 3.);
+          const double profile = n * n * q_0 * q_0 / slope;
+          s[0] = orc::pow(profile, exponent);
+          s[1] = q_0;
+          return s;
+        }
         }
         return s;
+      }
+
+      /* initial_precomputations(point): the bathymetry of the configuration (0 if it has none) */
+      double bathymetry(const Vec<dim> &x) const
+      {
+        const auto tp = transform.point(x);
+        if (kind == InitialStateKind::sloping_friction)
+          return -p[0] * tp[0]; /* initial_state_sloping_friction.h:83-87 */
+        return 0.;
       }
 
       state_type initial_state(const Vec<dim> &x, double t) const

@@ -84,3 +84,37 @@ def test_sw_ritter_dam_break_verification(oracle):
         assert abs(err_fma[k] - ref[k]) <= 2e-5 * ref[k], (k, err_fma[k], ref[k])
         assert abs(err[k] - ref[k]) <= 2.0 * spread + 1e-8 * ref[k], (k, err[k], err_fma[k], ref[k])
         assert abs(err[k] - ref[k]) <= 2e-4 * ref[k], (k, err[k], ref[k])
+
+
+def test_sw_steady_incline_with_friction_verification(oracle):
+    """tests/shallow_water/verification-steady_incline-erk33-l9.{prm,output}: steady flow down an
+    inclined plane (bathymetry Z = -slope x) balanced by Manning friction, `dynamic` boundaries,
+    513 dofs, 81 ERK33 cycles.  Pins what the other goldens do not touch: star states and affine
+    shift over a non-flat bathymetry, the friction source with its stage weights, and the
+    Riemann-characteristic boundary condition.  The golden errors are round-off (Linf 2.4e-14):
+    the scheme is well balanced; the final time pins the tau sequence."""
+    n = 2**9
+    off = oracle.assemble([n], [0.0], [20.0 / n], [orc.DYNAMIC] * 2)
+    assert off.n == 513
+    sim = off.sw_sim(kind=orc.SW_SLOPING_FRICTION, direction=(1.0,), position=(0.0,), p=(1.0e-2, 1.0e-1),
+                     gravity=9.81, manning_friction_coefficient=1.0e-2, reference_water_depth=1.0,
+                     dry_state_relaxation_large=1.0e4, dry_state_relaxation_small=1.0e4,
+                     limit_on_kinetic_energy=0, limit_on_square_velocity=1)
+    sim.configure_time_integrator("erk 33", 0.5, 0.5, "none")
+    sim.set_error_components([0, 1])
+    sim.interpolate(0.0)
+    U0 = sim.get_U(0).reshape(-1, 2)[7].copy()
+    t, cycles = 0.0, 0
+    while t < 1.0:
+        t += sim.time_step(t)
+        cycles += 1
+    ref = dict(t=1.000593578808362, Linf=2.388278346583212e-14, L1=4.287451614926996e-15, L2=5.452329602107318e-15)
+    err = sim.errors(t)
+    print(cycles, t, err)
+    assert abs(t - ref["t"]) <= 1e-14 * ref["t"]
+    # round-off sized errors: same magnitude as the reference's, digits are noise
+    for k in ("Linf", "L1", "L2"):
+        assert err[k] <= 3.0 * ref[k], (k, err[k], ref[k])
+    # and the steady state really carries a bathymetry gradient and friction (not a trivial test)
+    h0 = (1.0e-2**2 * 1.0e-1**2 / 1.0e-2) ** (1.0 / (2.0 + 4.0 / 3.0))
+    assert abs(U0[0] - h0) < 1e-15 and abs(U0[1] - 0.1) < 1e-17
