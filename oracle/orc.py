@@ -85,7 +85,7 @@ SW_CIRCULAR_DAM_BREAK, SW_UNIFORM, SW_RITTER_DAM_BREAK, SW_SMOOTH_VORTEX, SW_SLO
 DO_NOTHING, PERIODIC, SLIP, NO_SLIP, DIRICHLET, DYNAMIC, DIRICHLET_MOMENTUM = range(7)
 
 # initial state kinds
-UNIFORM, CONTRAST, ISENTROPIC_VORTEX = 0, 1, 2
+UNIFORM, CONTRAST, ISENTROPIC_VORTEX, LEBLANC, RAREFACTION = 0, 1, 2, 3, 4
 
 SCHEMES = {"ssprk 22": 0, "ssprk 33": 1, "erk 11": 2, "erk 22": 3, "erk 33": 4, "erk 43": 5, "erk 54": 6}
 

@@ -306,7 +306,9 @@ namespace orc
 
   namespace euler
   {
-    enum class InitialStateKind { uniform = 0, contrast = 1, isentropic_vortex = 2 };
+    /* 0..2 match enum rj_initial_state_kind; leblanc / rarefaction exist in the oracle only (1D
+     * verification decks of the reference) */
+    enum class InitialStateKind { uniform = 0, contrast = 1, isentropic_vortex = 2, leblanc = 3, rarefaction = 4 };
 
     template <int dim>
     struct InitialValues {
@@ -358,6 +360,84 @@ namespace orc
           if constexpr (dim >= 2)
             s[2] = rho * v;
           s[dim + 1] = E;
+          return s;
+        }
+        case InitialStateKind::leblanc: {
+          /* euler/initial_state_leblanc.h:45-111 (gamma = 5/3 hard wired in the energy) */
+          const double primitive_left[3] = {1., 0., 2. / 3. * 1.e-1};
+          const double primitive_right[3] = {1.e-3, 0., 2. / 3. * 1.e-10};
+          constexpr double rarefaction_speed = 0.49578489518897934;
+          constexpr double contact_velocity = 0.62183867139173454;
+          constexpr double right_shock_speed = 0.82911836253346982;
+          constexpr double pre_contact_density = 5.4079335349316249e-02;
+          constexpr double post_contact_density = 3.9999980604299963e-03;
+          constexpr double contact_pressure = 0.51557792765096996e-03;
+          double prim[3];
+          const double x = point[0];
+          if (x <= -1.0 / 3.0 * t) {
+            for (int q = 0; q < 3; ++q)
+              prim[q] = primitive_left[q];
+          } else if (x < rarefaction_speed * t) {
+            const double chi = x / t;
+            prim[0] = std::pow(0.75 - 0.75 * chi, 3.0);
+            prim[1] = 0.75 * (1.0 / 3.0 + chi);
+            prim[2] = (1.0 / 15.0) * std::pow(0.75 - 0.75 * chi, 5.0);
+          } else if (x < contact_velocity * t) {
+            prim[0] = pre_contact_density;
+            prim[1] = contact_velocity;
+            prim[2] = contact_pressure;
+          } else if (x < right_shock_speed * t) {
+            prim[0] = post_contact_density;
+            prim[1] = contact_velocity;
+            prim[2] = contact_pressure;
+          } else {
+            for (int q = 0; q < 3; ++q)
+              prim[q] = primitive_right[q];
+          }
+          state_type s{};
+          s[0] = prim[0];
+          s[1] = prim[0] * prim[1];
+          s[dim + 1] = prim[2] / (5. / 3. - 1.) + 0.5 * prim[0] * prim[1] * prim[1];
+          return s;
+        }
+        case InitialStateKind::rarefaction: {
+          /* euler/initial_state_rarefaction.h:37-155 */
+          const double gamma = sys.gamma;
+          auto speed_of_sound = [&](double rho, double p) { return std::sqrt(gamma * p / rho); };
+          const double rho_left = 3.0, p_left = 1.0;
+          const double c_left = speed_of_sound(rho_left, p_left);
+          const double u_left = c_left;
+          const double rho_right = 0.5;
+          const double p_right = std::pow(rho_right / rho_left, gamma) * p_left;
+          const double c_right = speed_of_sound(rho_right, p_right);
+          const double u_right = u_left + 2.0 * (c_left - c_right) / (gamma - 1.0);
+          const double k1 = 2.0 / (gamma + 1.0);
+          const double k2 = ((gamma - 1.0) / ((gamma + 1.0) * c_left));
+          const double density_exponent = 2.0 / (gamma - 1.0);
+          const double k3 = c_left + ((gamma - 1.0) / 2.0) * u_left;
+          const double pressure_exponent = 2.0 * gamma / (gamma - 1.0);
+          const double x = point[0];
+          const double t_0 = 0.2 / (u_right - u_left);
+          const double tt = t_0 + t;
+          double prim[3];
+          if (x <= tt * (u_left - c_left)) {
+            prim[0] = rho_left;
+            prim[1] = u_left;
+            prim[2] = p_left;
+          } else if (x <= tt * (u_right - c_right)) {
+            const double chi = x / tt;
+            prim[0] = rho_left * std::pow(k1 + k2 * (u_left - chi), density_exponent);
+            prim[1] = k1 * (k3 + chi);
+            prim[2] = p_left * std::pow(k1 + k2 * (u_left - chi), pressure_exponent);
+          } else {
+            prim[0] = rho_right;
+            prim[1] = u_right;
+            prim[2] = p_right;
+          }
+          state_type s{};
+          s[0] = prim[0];
+          s[1] = prim[0] * prim[1];
+          s[dim + 1] = prim[2] / (gamma - 1.) + 0.5 * prim[0] * prim[1] * prim[1];
           return s;
         }
         }

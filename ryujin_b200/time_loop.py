@@ -235,8 +235,6 @@ class TimeLoop:
 
         # ---- F - HyperbolicModule
         F = p.subsection("F - HyperbolicModule")
-        if F.get_bool("cfl with boundary dofs", False):
-            raise NotOnThePath("cfl with boundary dofs")
         ind, lim, rie = F.subsection("indicator"), F.subsection("limiter"), F.subsection("riemann solver")
         mp = dict(indicator_evc_factor=ind.get_float("evc factor", 1.0), limiter_iterations=lim.get_int("iterations", 2),
                   limiter_newton_tolerance=lim.get_float("newton tolerance", 1.0e-10),

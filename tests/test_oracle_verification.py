@@ -108,3 +108,41 @@ def test_mass_conservation_time_series(oracle):
     err = np.abs(got - ref) / scale
     assert np.max(err[:, [1, 2, 4, 5, 6, 8]]) < 1e-12, np.max(err, axis=0)
     assert np.max(np.abs(got[:, 3])) < 1e-14 and np.max(err[:, 7]) < 1e-9
+
+
+@pytest.mark.parametrize(
+    "name,kind,position,gamma,t_final,ref",
+    [
+        ("leblanc", "LEBLANC", 0.326732673267, 1.66666666666667, 0.66666666666667,
+         dict(t=0.6666710022008712, Linf=0.2233117555967211, L1=0.01167724325117752, L2=0.03259102542735855)),
+        ("rarefaction", "RAREFACTION", 0.2, 1.4, 0.30558,
+         dict(t=0.3056208093406663, Linf=0.001236294603917117, L1=2.234263733795138e-05, L2=8.123947460631401e-05)),
+    ],
+)
+def test_euler_1d_verification_decks(oracle, name, kind, position, gamma, t_final, ref):
+    """tests/euler/verification-{leblanc,rarefaction}-1d-erk33-l6.{prm,mpirun=4.output}: 1D Euler,
+    1601 dofs, cfl 0.1, limiter relaxation factor 8, 8153 / 7137 cycles (Le Blanc: a 1e9 pressure
+    ratio).  The restatement reproduces the number of cycles, the final time to 1.3e-8 / 5e-10
+    and the error norms to 2e-6 / 2e-5 relative.  This residual is the same for the libm, VCL and
+    FMA builds of the oracle and is not explained by mesh coordinates (a 1e-12 perturbation of the
+    initial state moves t by 2e-9: an effective 3e-13 perturbation would account for it); the
+    goldens come from a 4-rank run.  Weaker pins than the 2D decks, asserted as such."""
+    from oracle import orc
+
+    n = 25 * 2**6
+    off = oracle.assemble([n], [0.0], [1.0 / n], [orc.DIRICHLET] * 2)
+    assert off.n == 1601
+    sim = off.euler_sim(kind=getattr(orc, kind), direction=(1.0,), position=(position,), gamma=gamma,
+                        limiter_relaxation_factor=8.0)
+    sim.configure_time_integrator("erk 33", 0.1, 0.1, "none")
+    sim.interpolate(0.0)
+    t, cycles = 0.0, 0
+    while t < t_final:
+        t += sim.time_step(t)
+        cycles += 1
+    err = sim.errors(t)
+    print(name, cycles, t, err)
+    assert abs(t - ref["t"]) <= 2e-8 * ref["t"]
+    for k in ("Linf", "L1", "L2"):
+        assert abs(err[k] - ref[k]) <= 3e-5 * ref[k], (k, err[k], ref[k])
+    assert sim.counters() == (0, 0)
