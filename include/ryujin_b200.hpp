@@ -94,6 +94,13 @@ namespace ryujin_b200
     /** prepare() is part of construction (scratch allocation), hyperbolic_module.template.h:53-86 */
     void prepare() const {}
 
+    /** initial_precomputed() of the reference (hyperbolic_module.h:259,309): the bathymetry of the
+     * shallow water equations, one value per owned row; ghost rows are exchanged inside */
+    void set_initial_precomputed(const double *owned_values) const
+    {
+      check(rj_hyperbolic_module_set_initial_precomputed(handle_, owned_values));
+    }
+
     /** hyperbolic_module.template.h:97-193 */
     void prepare_state_vector(StateVector &state_vector, double t) const
     {
@@ -176,6 +183,11 @@ namespace ryujin_b200
       return tau;
     }
     double efficiency() const { return rj_time_integrator_efficiency(handle_); }
+
+    /** how a cycle is driven: reference control flow, device resident, or CUDA graph replay
+     * (bit-identical results; see rj_stepping) */
+    void stepping(rj_stepping mode) { check(rj_time_integrator_set_stepping(handle_, static_cast<int>(mode))); }
+    rj_stepping stepping() const { return static_cast<rj_stepping>(rj_time_integrator_stepping(handle_)); }
 
   private:
     rj_time_integrator *handle_ = nullptr;

@@ -24,6 +24,14 @@ double erk33(HyperbolicModule &hm, StateVector &s, StateVector &T0, StateVector 
   s.swap(T2);
   return 3. * tau;
 }
+// the shallow water additions and the stepping switch are part of the surface
+void configure(HyperbolicModule &hm, TimeIntegrator &ti, const double *bathymetry)
+{
+  hm.set_initial_precomputed(bathymetry);
+  ti.stepping(RJ_STEPPING_GRAPH);
+  if (ti.stepping() != RJ_STEPPING_GRAPH)
+    std::printf("unexpected\n");
+}
 int main()
 {
   std::printf("%s devices=%d\n", rj_version(), rj_device_count());
