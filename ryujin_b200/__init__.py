@@ -21,6 +21,7 @@ from .hyperbolic_module import (  # noqa: F401
     TimeSteppingScheme,
 )
 from .offline_data import Boundary, CartesianMesh, HostOfflineData, OfflineData  # noqa: F401
+from .stencil_io import StencilData  # noqa: F401
 from .time_loop import NotOnThePath, TimeLoop  # noqa: F401
 
 

@@ -168,6 +168,16 @@ class OfflineData:
     def from_mesh(cls, mesh, rank=0, n_ranks=1, device=0):
         return cls(HostOfflineData(mesh, rank, n_ranks), device)
 
+    @classmethod
+    def from_stencil(cls, stencil, device=0, host_layout_only=False):
+        """stencil: a stencil_io.StencilData or the path of an RJSTENCIL1 dump (arrays of a mesh
+        that was assembled elsewhere, e.g. by a ryujin build with deal.II)"""
+        from .stencil_io import StencilData
+
+        if isinstance(stencil, str):
+            stencil = StencilData.load(stencil)
+        return cls(stencil, device, host_layout_only)
+
     # accessors in the reference's vocabulary (offline_data.h:136-169)
     @property
     def n_export_indices(self):
