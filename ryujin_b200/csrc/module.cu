@@ -242,7 +242,7 @@ struct rj_hyperbolic_module {
   enum ProfSlot {
     P_BC = 0,
     P_PRECOMPUTE,
-    P_DIJ_ALPHA,
+    P_DIJ,
     P_ALPHA,
     P_BOUNDARY_DIJ,
     P_DII_TAU,
@@ -661,7 +661,7 @@ namespace rjb
       launch(k_reset_scalars, 1, 1, scalars);
 
       /* Step 2: d_ij (j > i), alpha_i; then C3 */
-      tag(P_DIJ_ALPHA);
+      tag(P_DIJ);
       {
         constexpr int W = RJ_DIJ_W; /* warps per slice in the edge-parallel d_ij kernel */
         launch(k_dij<Eq, W>, size_t(od->n_slices) * 32 * W, 32 * W, v, prm, 0u, od->n_slices, old_state.U, old_state.prec, dij);

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import ryujin_b200 as rj
+from helpers import make_mesh
 from oracle import orc
 
 B = rj.Boundary
@@ -211,3 +212,25 @@ def test_no_cpu_fallback():
     mesh = rj.CartesianMesh([4, 4], [0.0, 0.0], [1.0, 1.0], [B.slip] * 4)
     with pytest.raises(rj.NoDeviceError):
         rj.OfflineData.from_mesh(mesh)
+
+
+@pytest.mark.parametrize("case,n_cells,ranks", [("sod2d", [17, 23], 2), ("sod3d", [6, 5, 13], 3), ("step", None, 3)])
+def test_export_rows_are_exactly_the_rows_that_touch_ghosts(case, n_cells, ranks):
+    """The two-stream overlap launches rows [0, n_export) before the halo
+    exchange and the remaining rows concurrently with it.  That is only correct if (a) every row
+    that reads a ghost column and (b) every row that is sent to a neighbour lies in [0, n_export)
+    (offline_data.h:136-169: export indices come first)."""
+    import ryujin_b200 as rj
+
+    mesh = rj.CartesianMesh.forward_facing_step(1) if case == "step" else make_mesh(case, n_cells)
+    for rank in range(ranks):
+        host = rj.HostOfflineData(mesh, rank, ranks)
+        rows = np.repeat(np.arange(host.n_owned), np.diff(host.row_starts.astype(np.int64)))
+        touches_ghost = np.unique(rows[host.cols >= host.n_owned])
+        assert host.n_export <= host.n_owned
+        if len(touches_ghost):
+            assert touches_ghost.max() < host.n_export
+        if len(host.send_indices):
+            assert host.send_indices.max() < host.n_export
+        # and the range is tight: every export row is sent somewhere
+        assert np.array_equal(np.unique(host.send_indices), np.arange(host.n_export))
