@@ -14,6 +14,13 @@
 
 #define RJ_DEVICE __device__ __forceinline__
 
+/* The one place where kernels are launched (module.cu: launch()).  tests/host_emulation/ shadows
+ * <cuda_runtime.h> and defines this macro to run the same kernel source on the host (CI without
+ * a GPU); the product is only ever built by nvcc with the definition below. */
+#ifndef RJ_LAUNCH_KERNEL
+#define RJ_LAUNCH_KERNEL(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace rjb
 {
   constexpr int warp_size = 32; /* slice height C of the sliced-ELL layout */

@@ -228,12 +228,12 @@ struct rj_hyperbolic_module {
         RJ_CUDA(cudaEventCreate(&prof_events[prof_used + 1]));
       }
       RJ_CUDA(cudaEventRecord(prof_events[prof_used], cur));
-      kernel<<<grid, block, 0, cur>>>(args...);
+      RJ_LAUNCH_KERNEL(kernel, grid, block, cur, args...);
       RJ_CUDA(cudaEventRecord(prof_events[prof_used + 1], cur));
       prof_slots.push_back(prof_slot);
       prof_used += 2;
     } else
-      kernel<<<grid, block, 0, cur>>>(args...);
+      RJ_LAUNCH_KERNEL(kernel, grid, block, cur, args...);
     RJ_CUDA(cudaGetLastError());
     ++launches;
   }
