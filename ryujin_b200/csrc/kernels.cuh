@@ -54,6 +54,9 @@
 #define RJ_HO2_COND(col, len) ((col) < (len))
 #define RJ_HO2_NEXT(col) (++(col))
 #endif
+#ifndef RJ_PREFETCH_INDEX
+#define RJ_PREFETCH_INDEX 0
+#endif
 #ifndef RJ_DIJ_W
 #define RJ_DIJ_W 4 /* warps per slice of the edge-parallel d_ij kernel */
 #endif
@@ -140,6 +143,27 @@ namespace rjb
     for (int q = 0; q < k; ++q)
       v[size_t(q) * ld + i] = in[q];
   }
+
+  /* Software pipelining of the index -> gather chain of the row-parallel sweeps (experimental,
+   * RJ_PREFETCH_INDEX=1, not measured yet): the column (or transposed) index of the NEXT column is
+   * loaded before the gathers of the current one are consumed, so that the two dependent memory
+   * latencies of an iteration overlap.  Same loads, same arithmetic, different issue order.  With
+   * the default 0 the macros expand to the plain indexed load. */
+#if RJ_PREFETCH_INDEX
+  RJ_DEVICE uint32_t
+  pipelined_index(const uint32_t *__restrict__ idx, uint32_t e, uint32_t col, uint32_t len, uint32_t &next)
+  {
+    const uint32_t current = next;
+    if (col + 1 < len)
+      next = idx[e + 32];
+    return current;
+  }
+#define RJ_INDEX_INIT(name, idx, e0) uint32_t name = (idx)[e0];
+#define RJ_INDEX(name, idx, e, col, len) pipelined_index((idx), (e), (col), (len), name)
+#else
+#define RJ_INDEX_INIT(name, idx, e0)
+#define RJ_INDEX(name, idx, e, col, len) (idx)[e]
+#endif
 
   /* common row prologue: returns false if the thread has no row to work on */
   struct RowInfo {
@@ -363,10 +387,11 @@ namespace rjb
     typename Eq::Indicator indicator;
     indicator.reset(prm, prec_i, U_i);
 
+    RJ_INDEX_INIT(j_next, v.cols, r.base)
     RJ_UNROLL(RJ_UNROLL_ALPHA)
     for (uint32_t col = 0; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
-      const uint32_t j = v.cols[e];
+      const uint32_t j = RJ_INDEX(j_next, v.cols, e, col, r.len);
       double U_j[k], prec_j[np], aux_j[na], c_ij[dim];
       load_state<k>(U, v.ld, j, U_j);
       load_state<np>(prec, v.ld, j, prec_j);
@@ -651,10 +676,11 @@ namespace rjb
       }
     }
 
+    RJ_INDEX_INIT(j_next, v.cols, r.base)
     RJ_UNROLL(RJ_UNROLL_LOW)
     for (uint32_t col = 0; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
-      const uint32_t j = v.cols[e];
+      const uint32_t j = RJ_INDEX(j_next, v.cols, e, col, r.len);
 
       double U_j[k], prec_j[np], c_ij[dim];
       load_state<k>(U, v.ld, j, U_j);
@@ -828,10 +854,11 @@ namespace rjb
     const double factor = tau * m_i_inv * lambda_inv;
 
     bool all_ok = true;
+    RJ_INDEX_INIT(j_next, v.cols, r.base + 32) /* r.len > 1 */
     RJ_UNROLL(RJ_UNROLL_PIJ)
     for (uint32_t col = 1; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
-      const uint32_t j = v.cols[e];
+      const uint32_t j = RJ_INDEX(j_next, v.cols, e, col, r.len);
       double P_ij[k], F_jH[k];
 #pragma unroll
       for (int q = 0; q < k; ++q)
@@ -885,10 +912,11 @@ namespace rjb
     load_state<k>(U_new, v.ld, i, U_i_new);
     const double lambda = 1. / double(r.len - 1);
 
+    RJ_INDEX_INIT(eT_next, v.transposed, r.base + 32) /* r.len > 1 */
     RJ_UNROLL(RJ_UNROLL_HO1)
     for (uint32_t col = 1; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
-      const double l_ij = fmin(lij[e], lij[v.transposed[e]]);
+      const double l_ij = fmin(lij[e], lij[RJ_INDEX(eT_next, v.transposed, e, col, r.len)]);
       const double ll = l_ij * lambda;
 #pragma unroll
       for (int q = 0; q < k; ++q)
