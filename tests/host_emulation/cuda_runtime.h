@@ -12,6 +12,8 @@
 // their CUDA meaning (a thread that has exited counts as arrived).  "Device memory" is host
 // memory, streams are synchronous, events are time stamps.  Stream capture is NOT emulated
 // (cudaStreamBeginCapture fails): run with RYUJIN_B200_STEPPING=device or host.
+// All engine state is thread_local: several ranks can run as host threads of one process, with
+// the in-process NCCL emulation of nccl.h carrying the halo exchanges between them.
 #pragma once
 
 #include <chrono>
@@ -30,12 +32,12 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local
 
 struct rj_emu_dim3 {
   unsigned int x = 1, y = 1, z = 1;
 };
-extern rj_emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+extern thread_local rj_emu_dim3 threadIdx, blockIdx, blockDim, gridDim; /* one emulated device per host thread */
 
 /* ---- error type and memory ---- */
 typedef int cudaError_t;

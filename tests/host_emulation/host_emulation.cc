@@ -4,7 +4,7 @@
 
 #include <stdexcept>
 
-rj_emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local rj_emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 namespace
 {
@@ -22,12 +22,12 @@ namespace
     unsigned long long buffer[2][32];
   };
 
-  ucontext_t scheduler_context;
-  std::vector<Thread> threads;
-  Warp warps[32];
-  rj_emu_thunk *kernel_call = nullptr;
-  unsigned int current = 0, block_threads = 0, block_done = 0, block_arrived = 0;
-  unsigned long block_generation = 0;
+  thread_local ucontext_t scheduler_context;
+  thread_local std::vector<Thread> threads;
+  thread_local Warp warps[32];
+  thread_local rj_emu_thunk *kernel_call = nullptr;
+  thread_local unsigned int current = 0, block_threads = 0, block_done = 0, block_arrived = 0;
+  thread_local unsigned long block_generation = 0;
 
   void yield() { swapcontext(&threads[current].context, &scheduler_context); }
 
@@ -122,4 +122,139 @@ void rj_emu_run_grid(unsigned int grid, unsigned int block, rj_emu_thunk &call)
     blockIdx.x = b;
     run_block();
   }
+}
+
+
+/* ------------------------------------------------------------------------------------------ *
+ * In-process NCCL emulation (nccl.h): ranks are host threads.
+ * ------------------------------------------------------------------------------------------ */
+#include "nccl.h"
+
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+
+namespace
+{
+  struct World {
+    std::mutex mutex;
+    std::condition_variable changed;
+    int n_ranks = 0;
+    std::map<std::pair<int, int>, std::deque<std::vector<char>>> mailbox; /* (source, destination) */
+    /* all-reduce rendezvous */
+    int arrived = 0;
+    unsigned long generation = 0;
+    std::vector<char> accumulator, result;
+  };
+
+  std::mutex registry_mutex;
+  std::map<std::string, std::shared_ptr<World>> registry;
+  unsigned long next_id = 1;
+
+  size_t type_size(ncclDataType_t t) { return t == ncclDouble ? 8 : 4; }
+
+  template <typename T> void reduce_into(T *acc, const T *in, size_t n, ncclRedOp_t op)
+  {
+    for (size_t q = 0; q < n; ++q)
+      acc[q] = op == ncclMin ? std::min(acc[q], in[q]) : std::max(acc[q], in[q]);
+  }
+} // namespace
+
+struct rj_emu_comm {
+  std::shared_ptr<World> world;
+  int rank = 0;
+};
+
+const char *ncclGetErrorString(ncclResult_t r) { return r == ncclSuccess ? "no error" : "invalid use of the NCCL emulation"; }
+
+ncclResult_t ncclGetUniqueId(ncclUniqueId *id)
+{
+  std::lock_guard<std::mutex> lock(registry_mutex);
+  std::memset(id->internal, 0, sizeof(id->internal));
+  const std::string text = "rj-emu-" + std::to_string(next_id++);
+  std::memcpy(id->internal, text.data(), text.size());
+  return ncclSuccess;
+}
+
+ncclResult_t ncclCommInitRank(ncclComm_t *comm, int n_ranks, ncclUniqueId id, int rank)
+{
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks)
+    return ncclInvalidUsage;
+  const std::string key(id.internal, strnlen(id.internal, sizeof(id.internal)));
+  std::lock_guard<std::mutex> lock(registry_mutex);
+  auto &w = registry[key];
+  if (!w) {
+    w = std::make_shared<World>();
+    w->n_ranks = n_ranks;
+  }
+  if (w->n_ranks != n_ranks)
+    return ncclInvalidUsage;
+  *comm = new rj_emu_comm{w, rank};
+  return ncclSuccess;
+}
+
+ncclResult_t ncclCommDestroy(ncclComm_t comm)
+{
+  delete comm;
+  return ncclSuccess;
+}
+
+ncclResult_t ncclGroupStart() { return ncclSuccess; }
+ncclResult_t ncclGroupEnd() { return ncclSuccess; }
+
+ncclResult_t ncclSend(const void *buffer, size_t count, ncclDataType_t type, int peer, ncclComm_t comm, cudaStream_t)
+{
+  World &w = *comm->world;
+  std::vector<char> message(count * type_size(type));
+  std::memcpy(message.data(), buffer, message.size());
+  {
+    std::lock_guard<std::mutex> lock(w.mutex);
+    w.mailbox[{comm->rank, peer}].push_back(std::move(message));
+  }
+  w.changed.notify_all();
+  return ncclSuccess;
+}
+
+ncclResult_t ncclRecv(void *buffer, size_t count, ncclDataType_t type, int peer, ncclComm_t comm, cudaStream_t)
+{
+  World &w = *comm->world;
+  std::unique_lock<std::mutex> lock(w.mutex);
+  auto &queue = w.mailbox[{peer, comm->rank}];
+  w.changed.wait(lock, [&] { return !queue.empty(); });
+  std::vector<char> message = std::move(queue.front());
+  queue.pop_front();
+  if (message.size() != count * type_size(type))
+    return ncclInvalidUsage; /* sender and receiver disagree on the message size */
+  std::memcpy(buffer, message.data(), message.size());
+  return ncclSuccess;
+}
+
+ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataType_t type, ncclRedOp_t op, ncclComm_t comm, cudaStream_t)
+{
+  World &w = *comm->world;
+  const size_t bytes = count * type_size(type);
+  std::unique_lock<std::mutex> lock(w.mutex);
+  const unsigned long my_generation = w.generation;
+  if (w.arrived == 0) {
+    w.accumulator.assign(static_cast<const char *>(send), static_cast<const char *>(send) + bytes);
+  } else {
+    if (w.accumulator.size() != bytes)
+      return ncclInvalidUsage;
+    if (type == ncclDouble)
+      reduce_into(reinterpret_cast<double *>(w.accumulator.data()), static_cast<const double *>(send), count, op);
+    else
+      reduce_into(reinterpret_cast<int *>(w.accumulator.data()), static_cast<const int *>(send), count, op);
+  }
+  if (++w.arrived == w.n_ranks) {
+    w.result = w.accumulator;
+    w.arrived = 0;
+    ++w.generation;
+    w.changed.notify_all();
+  } else
+    w.changed.wait(lock, [&] { return w.generation != my_generation; });
+  std::memcpy(recv, w.result.data(), bytes);
+  return ncclSuccess;
 }

@@ -87,3 +87,17 @@ def test_fuzz_shallow_water_kernels_against_the_oracle():
     build()
     worst = run_fuzz("fuzz_shallow_water.py", 12, 16)
     assert all(v == 0.0 for v in worst.values()), worst
+
+
+def test_multi_rank_module_path_with_ranks_as_threads():
+    """SURVEY 8(e) on a CPU box: 3 ranks (one of them interior, two neighbours) as host threads,
+    each with its own emulated device, NCCL emulated in process -- the gathered state against the
+    single-rank run (the reference's partition round-off), overlap on / off bitwise, identical tau
+    and restart counters on every rank (tests/host_emulation/multi_rank_threads.py)."""
+    build()
+    env = dict(os.environ, RYUJIN_B200_LIB=EMU_LIB, RYUJIN_B200_STEPPING="device")
+    out = subprocess.run([sys.executable, os.path.join(EMU_DIR, "multi_rank_threads.py"), "3"], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "multi-rank parity ok" in out.stdout
+    assert out.stdout.count("overlap on/off bit-identical True") == 4
