@@ -13,7 +13,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 # on a many-core box that is shared with other jobs 64+ spinning threads per parallel region
 # cost minutes.  Must be set before libgomp is loaded.
 os.environ.setdefault("OMP_NUM_THREADS", str(min(8, os.cpu_count() or 1)))
-os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+if (os.cpu_count() or 1) > 16:
+    # a big box that is shared with other tenants (the GPU boxes: 128 hardware threads, a quota of
+    # 16): spinning threads steal from each other; on a small dedicated box spinning is 4x faster
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
 
 def pytest_configure(config):
