@@ -284,3 +284,25 @@ def sw_bathymetry(host, amplitude=0.2):
     if host.dim >= 2:
         z = z * np.sin(0.7 * x[:, 1] + 0.3) + 0.05 * x[:, 1] / 5.0
     return np.ascontiguousarray(z)
+
+
+# ---------------------------------------------------------------------------------------
+# cases added after a line-coverage run of the kernels (tests/host_emulation, gcov): Euler in 1D and
+# the `dynamic` (Riemann characteristic) boundary condition were not reached by any GPU test
+CASES.update({
+    "sod1d": dict(
+        dim=1, bottom_left=[0.0], top_right=[1.0], boundary=[B_DIRICHLET, B_DIRICHLET],
+        iv=dict(kind="contrast", direction=[1.0], position=[0.5], primitive=[1.0, 0.0, 1.0], primitive_right=[0.125, 0.0, 0.1]),
+    ),
+    # uniform Mach 0.5 flow at an angle through a box with `dynamic` boundaries on all sides:
+    # subsonic inflow on two sides, subsonic outflow on the other two
+    "dynamic2d": dict(
+        dim=2, bottom_left=[0.0, 0.0], top_right=[1.0, 1.0], boundary=[B_DYNAMIC] * 4,
+        iv=dict(kind="uniform", direction=[1.0, 0.5], position=[0.0, 0.0], primitive=[1.4, 0.5, 1.0]),
+    ),
+    # the same box with a Mach 3 flow: supersonic inflow / outflow branches
+    "dynamic2d_supersonic": dict(
+        dim=2, bottom_left=[0.0, 0.0], top_right=[1.0, 1.0], boundary=[B_DYNAMIC] * 4,
+        iv=dict(kind="uniform", direction=[1.0, 0.3], position=[0.0, 0.0], primitive=[1.4, 3.0, 1.0]),
+    ),
+})

@@ -489,3 +489,60 @@ def test_stepping_modes_are_bit_identical(scheme):
         assert (nr, nw) == (nr0, nw0), mode
     captured, replayed = results[rj.Stepping.graph][4]
     assert replayed >= len(taus0) and 1 <= captured <= 8
+
+
+@pytest.mark.parametrize("case,n_cells", [("sod1d", [200]), ("dynamic2d", [24, 20]), ("dynamic2d_supersonic", [20, 24])])
+def test_euler_1d_and_dynamic_boundary_parity(oracle, case, n_cells):
+    """Euler in 1D and the `dynamic` boundary condition (euler/hyperbolic_system.h:1040-1159,
+    subsonic and supersonic in/outflow through Riemann characteristics): a perturbed state so that
+    the prescribed data and the interior state differ, one update with every intermediate, then
+    ten ERK33 cycles."""
+    od, module, off, sim = gpu_and_oracle(oracle, case, n_cells)
+    old, new = module.state_vector(), module.state_vector()
+    old.interpolate(0.0)
+    U0 = old.download()
+    x = od.host.positions
+    bump = 1.0 + 0.2 * np.sin(7.0 * x[:, 0] + 0.3) * (np.cos(5.0 * x[:, 1]) if od.host.dim > 1 else 1.0)
+    U0 = U0 * bump[:, None]
+    old.upload(U0)
+    sim.set_U(U0, 0)
+    module.prepare_state_vector(old, 0.0)
+    sim.prepare_state_vector(0, 0.0)
+    assert rel_linf(old.download(), sim.get_U(0)) < 4e-15
+    if "dynamic" in case:
+        assert rel_linf(old.download(), U0) > 1e-3  # the boundary condition did something
+    module.cfl = 0.5
+    sim.set_cfl(0.5)
+    tau = module.step(old, [], [], new)
+    tau_ref = sim.step(0, [], [], 1)
+    assert abs(tau - tau_ref) <= 1e-14 * tau_ref
+    k = module.k
+    assert np.max(np.abs(module.scratch("alpha") - sim.scratch("alpha"))) < 2e-13
+    assert np.max(rel_linf_per_component(module.scratch("bounds").reshape(-1, 3), sim.scratch("bounds").reshape(-1, 3))) < 2e-13
+    assert np.max(rel_linf_per_component(module.scratch("r").reshape(-1, k), sim.scratch("r").reshape(-1, k))) < 1e-12
+    assert rel_linf(new.download(), sim.get_U(1)) < 1e-13
+    # a few cycles through the time integrator
+    od2, module2 = make_product(case, n_cells)
+    sims = [make_oracle(oracle, case, od2.host)[1]]
+    state, taus, refs = run_cycles(module2, sims, 10, "erk 33", cfl_min=0.3, cfl_max=0.3, recovery="none")
+    assert np.max(np.abs(taus - refs[0]) / refs[0]) < 1e-12
+    assert rel_linf(state.download(), sims[0].get_U(0)) < 1e-10
+
+
+def test_numeric_error_is_reported_like_the_reference():
+    """tau_max that is not positive (here: the caller's bound t_final - t = 0) trips the AssertThrow
+    of hyperbolic_module.template.h:573-576 -> RJ_ERR_NUMERIC with the reference's message, from
+    step() and from the device-resident cycle of the TimeIntegrator"""
+    import ryujin_b200 as rj
+
+    for through_integrator in (False, True):
+        od, module = make_product("sod2d", [16, 8])
+        state, new = module.state_vector(), module.state_vector()
+        state.interpolate(0.0)
+        with pytest.raises(rj.RyujinError) as err:
+            if through_integrator:
+                rj.TimeIntegrator(module).step(state, 0.05, t_final=0.05)
+            else:
+                module.prepare_state_vector(state, 0.0)
+                module.step(state, [], [], new, tau=0.0, tau_max=0.0)
+        assert err.value.code == -4 and "I'm sorry, Dave" in str(err.value)

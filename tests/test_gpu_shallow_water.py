@@ -5,7 +5,7 @@ the reference's goldens in test_oracle_shallow_water.py).  Needs a B200: `-m gpu
 import numpy as np
 import pytest
 
-from helpers import (SW_CASES, make_sw_oracle, make_sw_product, rel_linf, rel_linf_per_component, sw_bathymetry)
+from helpers import (B_DYNAMIC, SW_CASES, make_sw_oracle, make_sw_product, rel_linf, rel_linf_per_component, sw_bathymetry)
 
 pytestmark = pytest.mark.gpu
 
@@ -242,3 +242,58 @@ def test_sw_smooth_vortex_verification_golden_on_gpu(oracle):
     assert abs(t - ref["t"]) <= 1e-12 * ref["t"]
     for key in ("Linf", "L1", "L2"):
         assert abs(err[key] - ref[key]) <= 1e-8 * ref[key], (key, err[key], ref[key])
+
+
+SW_CASES.update({
+    # supersonic (Froude 3) uniform flow through `dynamic` boundaries, both velocity limiters off
+    # (the reference then returns t_l = 0 after the depth limiter, limiter.template.h:144-146)
+    "sw_supercritical": dict(
+        dim=2, bottom_left=[0.0, 0.0], top_right=[2.0, 1.0], boundary=[B_DYNAMIC] * 4,
+        iv=dict(kind="sw_uniform", direction=[1.0, 0.2], position=[0.0, 0.0], sw_params=[1.0, 9.5]),
+        eq=dict(gravity=9.81, reference_water_depth=1.0),
+        mp=dict(limit_on_kinetic_energy=0, limit_on_square_velocity=0),
+    ),
+})
+
+
+def test_sw_uniform_supercritical_dynamic_boundaries_and_limiters_off(oracle):
+    od, module, off, sim = gpu_and_oracle(oracle, "sw_supercritical", [24, 12], bathymetry=True)
+    old, new = module.state_vector(), module.state_vector()
+    old.interpolate(0.0)
+    U0 = old.download()
+    assert np.all(U0[:, 0] == 1.0)
+    x = od.host.positions
+    U0[:, 0] *= 1.0 + 0.1 * np.sin(5.0 * x[:, 0]) * np.cos(3.0 * x[:, 1])
+    old.upload(U0)
+    sim.set_U(U0, 0)
+    module.prepare_state_vector(old, 0.0)
+    sim.prepare_state_vector(0, 0.0)
+    assert rel_linf(old.download(), sim.get_U(0)) < 4e-15
+    module.cfl = 0.5
+    sim.set_cfl(0.5)
+    tau = module.step(old, [], [], new)
+    tau_ref = sim.step(0, [], [], 1)
+    assert abs(tau - tau_ref) <= 1e-14 * tau_ref
+    mask = np.ones(od.host.nnz, dtype=bool)
+    mask[od.host.row_starts[:-1].astype(np.int64)] = False
+    assert np.all(module.scratch("lij")[mask] == 0.0) and np.all(sim.scratch("lij")[mask] == 0.0)  # the quirk
+    assert rel_linf(new.download(), sim.get_U(1)) < 1e-13
+    assert (module.n_restarts(), module.n_warnings()) == sim.counters()
+
+
+def test_sw_limiter_failure_counts_like_the_oracle(oracle):
+    """an over-aggressive CFL number drives the low-order update out of the bounds: the `success`
+    flags of the depth / kinetic energy / velocity limiters (limiter.template.h:60-70,203-215,
+    349-360) turn into warnings exactly as in the oracle"""
+    od, module, off, sim = gpu_and_oracle(oracle, "sw_dam2d_friction", [20, 16], bathymetry=True)
+    old, new = module.state_vector(), module.state_vector()
+    old.interpolate(0.0)
+    sim.set_U(old.download(), 0)
+    module.prepare_state_vector(old, 0.0)
+    sim.prepare_state_vector(0, 0.0)
+    module.cfl = 6.0
+    sim.set_cfl(6.0)
+    module.step(old, [], [], new)
+    sim.step(0, [], [], 1)
+    assert (module.n_restarts(), module.n_warnings()) == sim.counters() == (0, 1)
+    assert rel_linf(new.download(), sim.get_U(1)) < 1e-12
