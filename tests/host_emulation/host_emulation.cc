@@ -3,6 +3,7 @@
 #include "cuda_runtime.h"
 
 #include <stdexcept>
+#include <string>
 
 thread_local rj_emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
@@ -28,6 +29,7 @@ namespace
   thread_local rj_emu_thunk *kernel_call = nullptr;
   thread_local unsigned int current = 0, block_threads = 0, block_done = 0, block_arrived = 0;
   thread_local unsigned long block_generation = 0;
+  thread_local bool reverse_threads = false;
 
   void yield() { swapcontext(&threads[current].context, &scheduler_context); }
 
@@ -60,7 +62,8 @@ namespace
     }
     std::vector<unsigned char> counted(block_threads, 0);
     while (block_done < block_threads) {
-      for (unsigned int t = 0; t < block_threads; ++t) {
+      for (unsigned int n = 0; n < block_threads; ++n) {
+        const unsigned int t = reverse_threads ? block_threads - 1 - n : n;
         if (counted[t])
           continue;
         current = t;
@@ -118,8 +121,29 @@ void rj_emu_run_grid(unsigned int grid, unsigned int block, rj_emu_thunk &call)
   block_threads = block;
   blockDim.x = block;
   gridDim.x = grid;
-  for (unsigned int b = 0; b < grid; ++b) {
-    blockIdx.x = b;
+  /* Order-dependence check (a poor man's race detector): RJ_EMU_ORDER=reverse runs the blocks of a
+   * launch from last to first and starts the threads of a block from the highest index;
+   * RJ_EMU_ORDER=shuffle visits the blocks in a pseudo-random order.  A kernel in which one thread
+   * consumes what another thread of the same launch produces gives different results then. */
+  static const std::string order = std::getenv("RJ_EMU_ORDER") ? std::getenv("RJ_EMU_ORDER") : "";
+  reverse_threads = (order == "reverse");
+  if (order == "shuffle") {
+    std::vector<unsigned int> perm(grid);
+    for (unsigned int b = 0; b < grid; ++b)
+      perm[b] = b;
+    unsigned long long state = 0x9e3779b97f4a7c15ull ^ grid;
+    for (unsigned int b = grid; b > 1; --b) {
+      state = state * 6364136223846793005ull + 1442695040888963407ull;
+      std::swap(perm[b - 1], perm[(state >> 33) % b]);
+    }
+    for (unsigned int b : perm) {
+      blockIdx.x = b;
+      run_block();
+    }
+    return;
+  }
+  for (unsigned int n = 0; n < grid; ++n) {
+    blockIdx.x = reverse_threads ? grid - 1 - n : n;
     run_block();
   }
 }
