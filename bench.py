@@ -424,6 +424,8 @@ def main():
     # torchrun exports OMP_NUM_THREADS=1; the host-side mesh generator and the CPU baseline are
     # OpenMP parallel: give every rank its share of the cores before the libraries load
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if "--impl" in sys.argv and "reference" in sys.argv:
+        world = 1  # the CPU arm runs on rank 0 alone (the other ranks exit): it may use every core
     if os.environ.get("OMP_NUM_THREADS", "1") == "1" or world > 1:
         os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(world, 1)))
     real_stdout = _quiet_stdout()
