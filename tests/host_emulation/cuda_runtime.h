@@ -47,8 +47,20 @@ inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ?
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-template <typename T> inline cudaError_t cudaMalloc(T **p, size_t n) { *p = static_cast<T *>(std::malloc(n ? n : 1)); return cudaSuccess; }
-template <typename T> inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = static_cast<T *>(std::malloc(n ? n : 1)); return cudaSuccess; }
+/* fresh "device" memory is poisoned (all bits set: NaN as double, 4294967295 as index) so that a kernel
+ * that consumes memory nobody initialised fails the parity tests instead of reading convenient zeros */
+template <typename T> inline cudaError_t cudaMalloc(T **p, size_t n)
+{
+  *p = static_cast<T *>(std::malloc(n ? n : 1));
+  std::memset(*p, 0xff, n ? n : 1);
+  return cudaSuccess;
+}
+template <typename T> inline cudaError_t cudaMallocHost(T **p, size_t n)
+{
+  *p = static_cast<T *>(std::malloc(n ? n : 1));
+  std::memset(*p, 0xff, n ? n : 1);
+  return cudaSuccess;
+}
 inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
