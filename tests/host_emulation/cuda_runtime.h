@@ -10,8 +10,10 @@
 // Execution model: a kernel launch runs its blocks one after the other; the threads of a block
 // are ucontext coroutines scheduled round-robin, so __syncthreads() and __shfl_xor_sync() have
 // their CUDA meaning (a thread that has exited counts as arrived).  "Device memory" is host
-// memory, streams are synchronous, events are time stamps.  Stream capture is NOT emulated
-// (cudaStreamBeginCapture fails): run with RYUJIN_B200_STEPPING=device or host.
+// memory, streams are synchronous, events are time stamps.  Stream capture records the kernel
+// launches, async copies and (emulated) NCCL calls issued between Begin/EndCapture as closures
+// without executing them; cudaGraphLaunch replays them in order -- the semantics the CUDA-graph
+// stepping of the TimeIntegrator relies on (arguments frozen at capture, data read at replay).
 // All engine state is thread_local: several ranks can run as host threads of one process, with
 // the in-process NCCL emulation of nccl.h carrying the halo exchanges between them.
 #pragma once
@@ -21,6 +23,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <ucontext.h>
 #include <vector>
 
@@ -69,8 +72,10 @@ inline cudaError_t cudaMemset(void *d, int v, size_t n) { std::memset(d, v, n); 
 /* ---- streams, events, graphs ---- */
 typedef struct rj_emu_stream *cudaStream_t;
 typedef struct rj_emu_event *cudaEvent_t;
-typedef struct rj_emu_graph *cudaGraph_t;
-typedef struct rj_emu_graph_exec *cudaGraphExec_t;
+struct rj_emu_graph;
+struct rj_emu_graph_exec;
+typedef rj_emu_graph *cudaGraph_t;
+typedef rj_emu_graph_exec *cudaGraphExec_t;
 struct rj_emu_stream { int id; };
 struct rj_emu_event { std::chrono::steady_clock::time_point t; };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaStreamCaptureModeRelaxed = 2 };
@@ -80,8 +85,27 @@ inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0;
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
-inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
-inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
+/* stream capture: closures recorded instead of executed */
+struct rj_emu_graph { std::vector<std::function<void()>> nodes; };
+struct rj_emu_graph_exec { std::vector<std::function<void()>> nodes; };
+extern thread_local rj_emu_graph *rj_emu_capture; /* non-null between Begin/EndCapture on this host thread */
+template <typename F> inline void rj_emu_enqueue(F f)
+{
+  if (rj_emu_capture)
+    rj_emu_capture->nodes.emplace_back(f);
+  else
+    f();
+}
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t)
+{
+  rj_emu_enqueue([=]() { std::memcpy(d, s, n); });
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t)
+{
+  rj_emu_enqueue([=]() { std::memset(d, v, n); });
+  return cudaSuccess;
+}
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new rj_emu_event(); return cudaSuccess; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new rj_emu_event(); return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
@@ -91,12 +115,32 @@ inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
   *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
   return cudaSuccess;
 }
-inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorNotSupported; }
-inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *g) { *g = nullptr; return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *, cudaGraph_t, unsigned long long) { return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
-inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
-inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int)
+{
+  if (rj_emu_capture)
+    return cudaErrorNotSupported;
+  rj_emu_capture = new rj_emu_graph();
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *g)
+{
+  *g = rj_emu_capture;
+  rj_emu_capture = nullptr;
+  return *g ? cudaSuccess : cudaErrorNotSupported;
+}
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *e, cudaGraph_t g, unsigned long long)
+{
+  *e = new rj_emu_graph_exec{g->nodes};
+  return cudaSuccess;
+}
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t)
+{
+  for (auto &node : e->nodes)
+    node();
+  return cudaSuccess;
+}
+inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete e; return cudaSuccess; }
 
 /* CUDA puts the C math classification functions into the global namespace */
 using std::isinf;
@@ -138,7 +182,10 @@ template <typename F> struct rj_emu_call : rj_emu_thunk {
 /* the one launch site of the product (module.cu: launch()) goes through this macro */
 #define RJ_LAUNCH_KERNEL(kernel, grid, block, stream, ...)                                                   \
   do {                                                                                                       \
-    auto rj_emu_body = [&]() { kernel(__VA_ARGS__); };                                                       \
-    rj_emu_call<decltype(rj_emu_body)> rj_emu_thunk_(rj_emu_body);                                           \
-    rj_emu_run_grid((grid), (block), rj_emu_thunk_);                                                         \
+    const unsigned int rj_emu_grid = (grid), rj_emu_block = (block);                                         \
+    rj_emu_enqueue([=]() {                                                                                   \
+      auto rj_emu_body = [&]() { kernel(__VA_ARGS__); };                                                     \
+      rj_emu_call<decltype(rj_emu_body)> rj_emu_thunk_(rj_emu_body);                                         \
+      rj_emu_run_grid(rj_emu_grid, rj_emu_block, rj_emu_thunk_);                                             \
+    });                                                                                                      \
   } while (0)

@@ -6,6 +6,7 @@
 #include <string>
 
 thread_local rj_emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local rj_emu_graph *rj_emu_capture = nullptr;
 
 namespace
 {
@@ -229,7 +230,47 @@ ncclResult_t ncclCommDestroy(ncclComm_t comm)
 ncclResult_t ncclGroupStart() { return ncclSuccess; }
 ncclResult_t ncclGroupEnd() { return ncclSuccess; }
 
+namespace
+{
+  ncclResult_t send_now(const void *buffer, size_t count, ncclDataType_t type, int peer, ncclComm_t comm);
+  ncclResult_t recv_now(void *buffer, size_t count, ncclDataType_t type, int peer, ncclComm_t comm);
+  ncclResult_t allreduce_now(const void *send, void *recv, size_t count, ncclDataType_t type, ncclRedOp_t op, ncclComm_t comm);
+  void must_succeed(ncclResult_t r)
+  {
+    if (r != ncclSuccess)
+      throw std::runtime_error("host emulation: NCCL call failed while a captured graph was replayed");
+  }
+} // namespace
+
+/* inside a stream capture the calls are recorded and run when the graph is launched */
 ncclResult_t ncclSend(const void *buffer, size_t count, ncclDataType_t type, int peer, ncclComm_t comm, cudaStream_t)
+{
+  if (rj_emu_capture) {
+    rj_emu_capture->nodes.emplace_back([=]() { must_succeed(send_now(buffer, count, type, peer, comm)); });
+    return ncclSuccess;
+  }
+  return send_now(buffer, count, type, peer, comm);
+}
+ncclResult_t ncclRecv(void *buffer, size_t count, ncclDataType_t type, int peer, ncclComm_t comm, cudaStream_t)
+{
+  if (rj_emu_capture) {
+    rj_emu_capture->nodes.emplace_back([=]() { must_succeed(recv_now(buffer, count, type, peer, comm)); });
+    return ncclSuccess;
+  }
+  return recv_now(buffer, count, type, peer, comm);
+}
+ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataType_t type, ncclRedOp_t op, ncclComm_t comm, cudaStream_t)
+{
+  if (rj_emu_capture) {
+    rj_emu_capture->nodes.emplace_back([=]() { must_succeed(allreduce_now(send, recv, count, type, op, comm)); });
+    return ncclSuccess;
+  }
+  return allreduce_now(send, recv, count, type, op, comm);
+}
+
+namespace
+{
+ncclResult_t send_now(const void *buffer, size_t count, ncclDataType_t type, int peer, ncclComm_t comm)
 {
   World &w = *comm->world;
   std::vector<char> message(count * type_size(type));
@@ -242,7 +283,7 @@ ncclResult_t ncclSend(const void *buffer, size_t count, ncclDataType_t type, int
   return ncclSuccess;
 }
 
-ncclResult_t ncclRecv(void *buffer, size_t count, ncclDataType_t type, int peer, ncclComm_t comm, cudaStream_t)
+ncclResult_t recv_now(void *buffer, size_t count, ncclDataType_t type, int peer, ncclComm_t comm)
 {
   World &w = *comm->world;
   std::unique_lock<std::mutex> lock(w.mutex);
@@ -256,7 +297,7 @@ ncclResult_t ncclRecv(void *buffer, size_t count, ncclDataType_t type, int peer,
   return ncclSuccess;
 }
 
-ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataType_t type, ncclRedOp_t op, ncclComm_t comm, cudaStream_t)
+ncclResult_t allreduce_now(const void *send, void *recv, size_t count, ncclDataType_t type, ncclRedOp_t op, ncclComm_t comm)
 {
   World &w = *comm->world;
   const size_t bytes = count * type_size(type);
@@ -282,3 +323,4 @@ ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataT
   std::memcpy(recv, w.result.data(), bytes);
   return ncclSuccess;
 }
+} // namespace

@@ -4,7 +4,7 @@ its own emulated device (tests/host_emulation/), the halo exchanges C1-C9 travel
 in-process NCCL emulation.  Same checks as tests/multi_gpu_parity.py on real GPUs: the gathered
 multi-rank state against the single-rank run, and overlap on / off bitwise.
 
-    RYUJIN_B200_LIB=tests/host_emulation/libryujin_b200_hostemu.so RYUJIN_B200_STEPPING=device \
+    RYUJIN_B200_LIB=tests/host_emulation/libryujin_b200_hostemu.so \
         python tests/host_emulation/multi_rank_threads.py [n_ranks]
 """
 import os

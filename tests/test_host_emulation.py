@@ -9,7 +9,7 @@ the `-m gpu` parity tests (GPU vs oracle, reference goldens, prm decks) run agai
 This is test infrastructure only: the product library is built by nvcc for sm_100a, has no host
 path for the kernels and fails with RJ_ERR_NO_DEVICE without a GPU
 (tests/test_offline_data.py::test_no_cpu_fallback).  On the GPU box the same tests run against
-the real library.  Not emulated: CUDA graphs (stepping is forced to "device"), NCCL (single rank).
+the real library.  Stream capture / graph replay and NCCL (ranks as host threads) are emulated too.
 """
 import os
 import re
@@ -21,7 +21,7 @@ EMU_DIR = os.path.join(ROOT, "tests", "host_emulation")
 EMU_LIB = os.path.join(EMU_DIR, "libryujin_b200_hostemu.so")
 
 # minutes-long on one host thread (66k..450k DoFs for hundreds of updates): left to the GPU
-HEAVY = ("conservation_and_symmetry or config1 or vortex_3d_cycles or golden_on_gpu or stepping_modes "
+HEAVY = ("conservation_and_symmetry or config1 or vortex_3d_cycles or golden_on_gpu "
          "or verification_goldens or decks_reproduce")
 
 
@@ -31,7 +31,7 @@ def build():
 
 
 def run_gpu_tests(selection, timeout=900):
-    env = dict(os.environ, RYUJIN_B200_LIB=EMU_LIB, RYUJIN_B200_STEPPING="device")
+    env = dict(os.environ, RYUJIN_B200_LIB=EMU_LIB)  # default stepping: CUDA graph replay (capture is emulated)
     cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-q", "-m", "gpu", "-k", selection,
            "-p", "no:cacheprovider"]
     out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
@@ -60,7 +60,7 @@ def test_one_reference_deck_and_golden_against_the_host_emulation():
 def run_fuzz(script, seed, cases, order=""):
     import json
 
-    env = dict(os.environ, RYUJIN_B200_LIB=EMU_LIB, RYUJIN_B200_STEPPING="device", RJ_EMU_ORDER=order)
+    env = dict(os.environ, RYUJIN_B200_LIB=EMU_LIB, RJ_EMU_ORDER=order)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fuzz", script), str(seed), str(cases)], cwd=ROOT, env=env,
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
@@ -95,7 +95,7 @@ def test_multi_rank_module_path_with_ranks_as_threads():
     single-rank run (the reference's partition round-off), overlap on / off bitwise, identical tau
     and restart counters on every rank (tests/host_emulation/multi_rank_threads.py)."""
     build()
-    env = dict(os.environ, RYUJIN_B200_LIB=EMU_LIB, RYUJIN_B200_STEPPING="device")
+    env = dict(os.environ, RYUJIN_B200_LIB=EMU_LIB)  # graph stepping: the NCCL calls are captured and replayed
     out = subprocess.run([sys.executable, os.path.join(EMU_DIR, "multi_rank_threads.py"), "3"], cwd=ROOT, env=env,
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]

@@ -12,9 +12,9 @@ for f in module device_offline; do
 done
 /usr/bin/g++ -shared -fopenmp -pthread --coverage -o build_cov/libemu_cov.so build_cov/module.o build_cov/device_offline.o \
   build/host_offline.o build/host_emulation.o
-( cd ../.. && RYUJIN_B200_LIB=$PWD/tests/host_emulation/build_cov/libemu_cov.so RYUJIN_B200_STEPPING=device \
+( cd ../.. && RYUJIN_B200_LIB=$PWD/tests/host_emulation/build_cov/libemu_cov.so \
   python -m pytest tests -q -m gpu -p no:cacheprovider \
-  -k "not (conservation_and_symmetry or config1 or vortex_3d_cycles or golden_on_gpu or stepping_modes or verification_goldens or decks_reproduce)" )
+  -k "not (conservation_and_symmetry or config1 or vortex_3d_cycles or golden_on_gpu or verification_goldens or decks_reproduce)" )
 gcov -b -o build_cov build_cov/module.gcda > build_cov/gcov.log 2>&1
 python - <<'PY'
 import re
