@@ -1,0 +1,26 @@
+#!/bin/bash
+# Build experimental flavours of libryujin_b200.so into gpurun_variants/ (they travel to the GPU
+# box with the snapshot; the directory is git-ignored through *.so).  Each line: name:nvcc flags.
+# Run here (no GPU needed), then `gpurun -- 'bash tools/gpu_variants.sh'` on the box.
+set -eu
+cd "$(dirname "$0")/../ryujin_b200/csrc"
+OUT=../../gpurun_variants
+mkdir -p "$OUT"
+VARIANTS=${VARIANTS:-"
+base:
+prefetch:-DRJ_PREFETCH_INDEX=1
+prefetch_alpha8:-DRJ_PREFETCH_INDEX=1 -DRJ_MB_ALPHA=8
+prefetch_alpha8_u2:-DRJ_PREFETCH_INDEX=1 -DRJ_MB_ALPHA=8 -DRJ_UNROLL_ALPHA=2
+prefetch_pij6:-DRJ_PREFETCH_INDEX=1 -DRJ_MB_PIJ=6
+prefetch_low_u2:-DRJ_PREFETCH_INDEX=1 -DRJ_UNROLL_LOW=2
+prefetch_low_u2_mb5:-DRJ_PREFETCH_INDEX=1 -DRJ_UNROLL_LOW=2 -DRJ_MB_LOW=5
+"}
+echo "$VARIANTS" | while IFS= read -r line; do
+  [ -z "$line" ] && continue
+  name=${line%%:*}; flags=${line#*:}
+  rm -f build/module.o
+  make -s EXTRA_NVFLAGS="$flags" OUT="$OUT/lib_$name.so" 2>&1 | grep -E "error" && exit 1
+  echo "built $name ($flags)"
+done
+rm -f build/module.o
+make -s   # restore the default object and library
