@@ -59,17 +59,13 @@ def test_oracle_assembled_arrays_import(oracle):
     assert np.allclose(data.mij, host.mij, rtol=1e-14, atol=0) and np.allclose(data.cij, host.cij, rtol=0, atol=1e-15)
 
 
-@pytest.mark.parametrize("simd_length", [2, 4, 8])
-def test_reference_simd_host_layout_is_accepted(oracle, simd_length):
-    """the arrays exactly as a ryujin build holds them (SIMD groups + CSR tail): the decoded
-    pattern and the resulting device layout equal those of the CSR description, and the encoder
-    used here agrees with the oracle's restatement of SparsityPatternSIMD::reinit"""
+def renumbered_csr_and_simd(simd_length, n_cells=(12, 10)):
+    """a 2D stencil renumbered so that the first n_internal rows have equal length (what the
+    reference's renumbering guarantees), as CSR arrays and in the reference's SIMD host layout"""
     import ryujin_b200 as rj
     from ryujin_b200.stencil_io import StencilData, encode_simd_layout
 
-    # a periodic-free interior block has equal row lengths only away from the boundary: build a
-    # pattern whose first rows are regular by renumbering interior rows first
-    mesh = make_mesh("sod2d", [12, 10])
+    mesh = make_mesh("sod2d", list(n_cells))
     host = rj.HostOfflineData(mesh)
     lengths = np.diff(host.row_starts.astype(np.int64))
     interior = np.where(lengths == 9)[0]
@@ -93,14 +89,24 @@ def test_reference_simd_host_layout_is_accepted(oracle, simd_length):
     bdof = new_of_old[host.boundary_dof]
     keep = np.argsort(bdof, kind="stable")
     common = dict(boundary_dof=bdof[keep], boundary_normal=host.boundary_normal[keep], boundary_id=host.boundary_id[keep],
-                  boundary_position=host.boundary_position[keep])
-
+                  boundary_position=host.boundary_position[keep], positions=host.positions[order])
     csr = StencilData.from_arrays(2, rp.astype(np.uint64), cols, mass, cij, mi, host.measure_of_omega, **common)
     rs, sc, sm, scij = encode_simd_layout(rp, cols, mass, cij, n_internal, simd_length)
-    o_rs, o_ci, _ = oracle.sparsity_simd(rp, cols, n_internal, simd_length)
-    assert np.array_equal(rs, o_rs) and np.array_equal(sc, o_ci)
     simd = StencilData.from_arrays(2, rs, sc, sm, scij, mi, host.measure_of_omega, n_owned=host.n_owned,
                                    n_internal=n_internal, simd_length=simd_length, **common)
+    return csr, simd, (rp, cols, n_internal, rs, sc)
+
+
+@pytest.mark.parametrize("simd_length", [2, 4, 8])
+def test_reference_simd_host_layout_is_accepted(oracle, simd_length):
+    """the arrays exactly as a ryujin build holds them (SIMD groups + CSR tail): the decoded
+    pattern and the resulting device layout equal those of the CSR description, and the encoder
+    used here agrees with the oracle's restatement of SparsityPatternSIMD::reinit"""
+    import ryujin_b200 as rj
+
+    csr, simd, (rp, cols, n_internal, rs, sc) = renumbered_csr_and_simd(simd_length)
+    o_rs, o_ci, _ = oracle.sparsity_simd(rp, cols, n_internal, simd_length)
+    assert np.array_equal(rs, o_rs) and np.array_equal(sc, o_ci)
     assert np.array_equal(simd.row_starts, rp) and np.array_equal(simd.cols, cols)
     assert layouts_equal(rj.OfflineData(simd, host_layout_only=True), rj.OfflineData(csr, host_layout_only=True))
 
@@ -144,3 +150,30 @@ def test_imported_stencil_runs_like_the_generated_one(tmp_path):
         results.append((t, state.download()))
     assert results[0][0] == results[1][0]
     assert np.array_equal(results[0][1], results[1][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("simd_length", [4, 8])
+def test_simd_host_layout_runs_like_the_csr_description(simd_length):
+    """the matrices handed over in the reference's SparseMatrixSIMD layout (mass matrix with one,
+    c_ij with dim components per entry) are decoded into the device layout exactly like the CSR
+    description: bit-identical states after three ERK33 cycles on a renumbered stencil"""
+    import ryujin_b200 as rj
+    from helpers import CASES
+
+    csr, simd, _ = renumbered_csr_and_simd(simd_length, n_cells=(20, 14))
+    iv = dict(CASES["sod2d"]["iv"])
+    kind = getattr(rj.InitialState, iv.pop("kind"))
+    results = []
+    for data in (csr, simd):
+        od = rj.OfflineData(data)
+        module = rj.HyperbolicModule(od, rj.HyperbolicSystem(), rj.InitialValues(kind, **iv))
+        ti = rj.TimeIntegrator(module)
+        state = module.state_vector()
+        state.interpolate(0.0)
+        t = 0.0
+        for _ in range(3):
+            t += ti.step(state, t)
+        results.append((t, state.download()))
+    assert results[0][0] == results[1][0] and np.array_equal(results[0][1], results[1][1])
+    assert np.max(np.abs(results[0][1][:, 0] - 1.0)) > 1e-3  # the shock tube did evolve
