@@ -546,3 +546,36 @@ def test_numeric_error_is_reported_like_the_reference():
                 module.prepare_state_vector(state, 0.0)
                 module.step(state, [], [], new, tau=0.0, tau_max=0.0)
         assert err.value.code == -4 and "I'm sorry, Dave" in str(err.value)
+
+
+def test_profiling_and_raw_pointer_transfers_do_not_change_results():
+    """what bench.py uses: per-kernel event timing (`set_profiling`, falls back from graph replay to
+    the device-resident cycle) and uploads / downloads through raw host pointers"""
+    import ctypes
+
+    import ryujin_b200 as rj
+
+    results = []
+    for profiling in (False, True):
+        od, module = make_product("sod2d", [32, 12])
+        ti = rj.TimeIntegrator(module)
+        state = module.state_vector()
+        state.interpolate(0.0)
+        U0 = np.ascontiguousarray(state.download())
+        state.upload_from_pointer(U0.ctypes.data_as(ctypes.c_void_p))
+        module.set_profiling(profiling)
+        t = 0.0
+        for _ in range(4):
+            t += ti.step(state, t)
+        prof = module.profile()
+        module.set_profiling(False)
+        out = np.zeros_like(U0)
+        state.download_to_pointer(out.ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(out, state.download())
+        results.append((t, out, prof))
+    assert results[0][0] == results[1][0] and np.array_equal(results[0][1], results[1][1])
+    off, on = results[0][2], results[1][2]
+    assert all(count == 0 for _, count in off.values())
+    # 4 ERK33 cycles = 12 updates: one launch of every sweep per update
+    for name in ("dij", "alpha", "low_order", "pij_lij", "high_order_next_lij", "high_order_final", "precompute"):
+        assert on[name][1] == 12 and on[name][0] > 0.0, (name, on[name])
