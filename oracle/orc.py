@@ -149,6 +149,8 @@ class Oracle:
             path = port
         elif variant == "fma":
             path = os.path.join(_HERE, "liboracle_fma.so")
+        elif variant == "rjpow":
+            path = os.path.join(_HERE, "liboracle_rjpow.so")
         else:
             path = variant  # explicit path of another build of the same sources (experiments)
         if not os.path.exists(path):

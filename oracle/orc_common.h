@@ -24,6 +24,14 @@
 #include <limits>
 #include <vector>
 
+#ifdef ORC_USE_RJ_POW
+// liboracle_rjpow.so only: the product's pow (ryujin_b200/csrc/accurate_pow.h, host path).  With
+// it the CPU restatement and the CUDA path execute literally the same operations, so a parity
+// test can demand BIT-IDENTICAL states over hundreds of updates; the libm build stays the
+// independent check of that pow (0.504 ulp, equal to libm in 99.97 % of all calls).
+#include "../ryujin_b200/csrc/accurate_pow.h"
+#endif
+
 #ifdef ORC_USE_VCL
 // oracle/_ref build only: Agner Fog's vector class library as vendored by the
 // reference (simd-math/, vectorclass/version2 @08959eb). Compiled from where it
@@ -40,8 +48,10 @@ namespace orc
 
   inline double pow(double x, double b)
   {
-#ifdef ORC_USE_VCL
+#if defined(ORC_USE_VCL)
     return ::pow(Vec2d(x), b).extract(0);
+#elif defined(ORC_USE_RJ_POW)
+    return rjb::rj_pow(x, b);
 #else
     return std::pow(x, b);
 #endif
