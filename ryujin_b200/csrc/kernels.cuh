@@ -57,6 +57,18 @@
 #ifndef RJ_PREFETCH_INDEX
 #define RJ_PREFETCH_INDEX 0
 #endif
+#ifndef RJ_ALPHA_EDGE
+#define RJ_ALPHA_EDGE 0 /* 1: edge-parallel alpha_i with an ordered reduction (experimental, not measured yet) */
+#endif
+#ifndef RJ_ALPHA_EDGE_W
+#define RJ_ALPHA_EDGE_W 4
+#endif
+#ifndef RJ_ALPHA_EDGE_MAXCOL
+#define RJ_ALPHA_EDGE_MAXCOL 27 /* longest row the shared memory stage is sized for (Q1 in 3D) */
+#endif
+#ifndef RJ_MB_ALPHA_EDGE
+#define RJ_MB_ALPHA_EDGE 5
+#endif
 #ifndef RJ_DIJ_W
 #define RJ_DIJ_W 4 /* warps per slice of the edge-parallel d_ij kernel */
 #endif
@@ -404,6 +416,84 @@ namespace rjb
 
     const double hd_i = v.mi[i] * v.measure_of_omega_inverse;
     alpha[i] = indicator.alpha(prm, hd_i);
+  }
+
+
+  /* ---------------------------------------------------------------------- *
+   * Experimental alternative to k_alpha (RJ_ALPHA_EDGE=1): EDGE parallel like k_dij.  A block is
+   * one slice of 32 rows x W warps; warp w evaluates the per-edge contributions of columns
+   * w, w+W, ... (the gathers of up to W columns of a row are in flight at once) into shared
+   * memory; warp 0 then adds them up IN COLUMN ORDER, exactly the additions of the row-parallel
+   * kernel, so the result is bit-identical (0 + x == x; the sign of a zero cannot differ because
+   * the accumulators start at +0).
+   * ---------------------------------------------------------------------- */
+  template <class Eq, int W, int MAXCOL>
+  __global__ void __launch_bounds__(32 * W, RJ_MB_ALPHA_EDGE) k_alpha_edge(StencilView v,
+                                                                         typename Eq::Params prm,
+                                                                         uint32_t slice_begin,
+                                                                         uint32_t slice_end,
+                                                                         const double *__restrict__ U,
+                                                                         const double *__restrict__ prec,
+                                                                         const double *__restrict__ aux,
+                                                                         double *__restrict__ alpha)
+  {
+    constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec, na = Eq::n_aux;
+    __shared__ double contribution[MAXCOL * (k + 1) * 32];
+    const uint32_t g = slice_begin + blockIdx.x;
+    if (g >= slice_end)
+      return; /* the whole block */
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t i = (g << 5) + lane;
+    const bool has_row = i < v.n_owned && v.row_length[i] > 1;
+    const uint32_t len = has_row ? v.row_length[i] : 0u;
+    const uint32_t base = v.slice_offsets[g] + lane;
+
+    double U_i[k], prec_i[np];
+    typename Eq::Indicator indicator;
+    if (has_row) {
+      load_state<k>(U, v.ld, i, U_i);
+      load_state<np>(prec, v.ld, i, prec_i);
+      indicator.reset(prm, prec_i, U_i);
+    }
+
+    for (uint32_t col = w; col < len; col += W) {
+      const uint32_t e = base + col * 32;
+      const uint32_t j = v.cols[e];
+      double U_j[k], prec_j[np], aux_j[na], c_ij[dim];
+      load_state<k>(U, v.ld, j, U_j);
+      load_state<np>(prec, v.ld, j, prec_j);
+      load_state<na>(aux, v.ld, j, aux_j);
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
+      indicator.left = 0.;
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        indicator.right[q] = 0.;
+      indicator.accumulate(prm, U_i, prec_i, U_j, prec_j, Eq::load_aux(aux_j), c_ij);
+      double *slot = contribution + size_t(col) * (k + 1) * 32 + lane;
+      slot[0] = indicator.left;
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        slot[(1 + q) * 32] = indicator.right[q];
+    }
+    __syncthreads();
+
+    if (w == 0 && has_row) {
+      indicator.left = 0.;
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        indicator.right[q] = 0.;
+      for (uint32_t col = 0; col < len; ++col) {
+        const double *slot = contribution + size_t(col) * (k + 1) * 32 + lane;
+        indicator.left += slot[0];
+#pragma unroll
+        for (int q = 0; q < k; ++q)
+          indicator.right[q] += slot[(1 + q) * 32];
+      }
+      const double hd_i = v.mi[i] * v.measure_of_omega_inverse;
+      alpha[i] = indicator.alpha(prm, hd_i);
+    }
   }
 
 

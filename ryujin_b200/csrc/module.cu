@@ -101,6 +101,7 @@ struct rj_hyperbolic_module {
   uint64_t launches = 0;
 
   int k = 0, n_prec = 0, n_bounds = 0, n_aux = 0;
+  uint32_t max_row_length = 0; /* longest stencil row (sizes the shared memory stage of k_alpha_edge) */
 
   /* scratch, hyperbolic_module.h:319-333 */
   double *alpha = nullptr, *bounds = nullptr, *r = nullptr;
@@ -669,7 +670,16 @@ namespace rjb
       sweep(
           [&](uint32_t b, uint32_t e) {
             tag(P_ALPHA);
-            launch_rows(k_alpha<Eq>, b, e, v, prm, b, e, old_state.U, old_state.prec, old_state.aux, alpha);
+#if RJ_ALPHA_EDGE
+            if (max_row_length <= RJ_ALPHA_EDGE_MAXCOL) {
+              constexpr int W = RJ_ALPHA_EDGE_W;
+              const uint32_t s0 = b / 32, s1 = (e + 31) / 32; /* b is slice aligned */
+              if (s1 > s0)
+                launch(k_alpha_edge<Eq, W, RJ_ALPHA_EDGE_MAXCOL>, size_t(s1 - s0) * 32 * W, 32 * W, v, prm, s0, s1,
+                       old_state.U, old_state.prec, old_state.aux, alpha);
+            } else
+#endif
+              launch_rows(k_alpha<Eq>, b, e, v, prm, b, e, old_state.U, old_state.prec, old_state.aux, alpha);
             if (e == n_owned && (b < e || b == 0)) {
               /* Step 3: boundary d_ij, d_ii, tau_max (need d_ij only) */
               tag(P_BOUNDARY_DIJ);
@@ -1342,6 +1352,8 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
 
     hm->od = od;
     hm->device = od->device;
+    for (uint32_t len : od->h_row_length)
+      hm->max_row_length = std::max(hm->max_row_length, len);
     hm->comm = comm;
     hm->eq = *eq;
     hm->mp = *mp;

@@ -14,6 +14,10 @@ prefetch_alpha8_u2:-DRJ_PREFETCH_INDEX=1 -DRJ_MB_ALPHA=8 -DRJ_UNROLL_ALPHA=2
 prefetch_pij6:-DRJ_PREFETCH_INDEX=1 -DRJ_MB_PIJ=6
 prefetch_low_u2:-DRJ_PREFETCH_INDEX=1 -DRJ_UNROLL_LOW=2
 prefetch_low_u2_mb5:-DRJ_PREFETCH_INDEX=1 -DRJ_UNROLL_LOW=2 -DRJ_MB_LOW=5
+alpha_edge:-DRJ_ALPHA_EDGE=1
+alpha_edge_w8:-DRJ_ALPHA_EDGE=1 -DRJ_ALPHA_EDGE_W=8 -DRJ_MB_ALPHA_EDGE=2
+alpha_edge_mb4:-DRJ_ALPHA_EDGE=1 -DRJ_MB_ALPHA_EDGE=4
+alpha_edge_prefetch:-DRJ_ALPHA_EDGE=1 -DRJ_PREFETCH_INDEX=1
 "}
 echo "$VARIANTS" | while IFS= read -r line; do
   [ -z "$line" ] && continue
