@@ -60,6 +60,24 @@
 #ifndef RJ_ALPHA_EDGE
 #define RJ_ALPHA_EDGE 0 /* 1: edge-parallel alpha_i with an ordered reduction (experimental, not measured yet) */
 #endif
+#ifndef RJ_PIJ_EDGE
+#define RJ_PIJ_EDGE 0 /* 1: edge-parallel step 5 (no reduction in that sweep at all) */
+#endif
+#ifndef RJ_PIJ_EDGE_W
+#define RJ_PIJ_EDGE_W 4
+#endif
+#ifndef RJ_MB_PIJ_EDGE
+#define RJ_MB_PIJ_EDGE 5
+#endif
+#ifndef RJ_HO_EDGE
+#define RJ_HO_EDGE 0 /* 1: edge-parallel step 6 with the slice's P_ij and l_ij staged in shared memory */
+#endif
+#ifndef RJ_HO_EDGE_W
+#define RJ_HO_EDGE_W 4
+#endif
+#ifndef RJ_MB_HO_EDGE
+#define RJ_MB_HO_EDGE 5
+#endif
 #ifndef RJ_ALPHA_EDGE_W
 #define RJ_ALPHA_EDGE_W 4
 #endif
@@ -977,6 +995,76 @@ namespace rjb
   }
 
 
+  /* Experimental alternative to k_pij_lij (RJ_PIJ_EDGE=1): the entries of a row are independent
+   * in this sweep (P_ij correction and l_ij = limit(...) per entry, one OR-reduced flag), so a
+   * block of W warps shares the 32 rows of a slice, warp w taking columns w, w+W, ...: W times more
+   * loads in flight per row, same bytes, same arithmetic per entry. */
+  template <class Eq, int W>
+  __global__ void __launch_bounds__(32 * W, RJ_MB_PIJ_EDGE) k_pij_lij_edge(StencilView v,
+                                                                         typename Eq::Params prm,
+                                                                         uint32_t slice_begin,
+                                                                         uint32_t slice_end,
+                                                                         const double *__restrict__ U_new,
+                                                                         const double *__restrict__ r_vec,
+                                                                         const double *__restrict__ bounds,
+                                                                         StepScalars *__restrict__ scalars,
+                                                                         double *__restrict__ pij,
+                                                                         double *__restrict__ lij)
+  {
+    constexpr int k = Eq::k, nb = Eq::n_bounds;
+    const uint32_t g = slice_begin + blockIdx.x;
+    if (g >= slice_end)
+      return;
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t i = (g << 5) + lane;
+    if (i >= v.n_owned)
+      return;
+    const uint32_t len = v.row_length[i];
+    if (len <= 1)
+      return;
+    const uint32_t base = v.slice_offsets[g] + lane;
+    const double tau = scalars->tau;
+
+    double b[nb], U_i_new[k], F_iH[k];
+    load_state<nb>(bounds, v.ld, i, b);
+    load_state<k>(U_new, v.ld, i, U_i_new);
+    load_state<k>(r_vec, v.ld, i, F_iH);
+    const double m_i_inv = v.mi_inv[i];
+    const double lambda_inv = double(len - 1);
+    const double factor = tau * m_i_inv * lambda_inv;
+
+    bool all_ok = true;
+    for (uint32_t col = 1 + w; col < len; col += W) {
+      const uint32_t e = base + col * 32;
+      const uint32_t j = v.cols[e];
+      double P_ij[k], F_jH[k];
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        P_ij[q] = pij[size_t(q) * v.E_owned + e];
+      load_state<k>(r_vec, v.ld, j, F_jH);
+
+      const double m_j_inv = v.mi_inv[j];
+      const double m_ij = v.mij[e];
+      const double b_ij = 0. - m_ij * m_j_inv;
+      const double b_ji = 0. - m_ij * m_i_inv;
+
+#pragma unroll
+      for (int q = 0; q < k; ++q) {
+        P_ij[q] += b_ij * F_jH[q] - b_ji * F_iH[q];
+        P_ij[q] *= factor;
+        pij[size_t(q) * v.E_owned + e] = P_ij[q];
+      }
+
+      bool success;
+      const double l_ij = Eq::limit(prm, b, U_i_new, P_ij, success);
+      lij[e] = l_ij;
+      all_ok = all_ok && success;
+    }
+    if (!all_ok)
+      atomicOr(&scalars->restart_needed, 1);
+  }
+
+
   /* ---------------------------------------------------------------------- *
    * Steps 6, 7: symmetrize l_ij, high-order update, next l_ij,
    * hyperbolic_module.template.h:1053-1182.
@@ -1030,6 +1118,89 @@ namespace rjb
 #pragma unroll
       for (int q = 0; q < k; ++q)
         new_p_ij[q] = (1. - old_l_ij) * pij[size_t(q) * v.E_owned + e];
+      bool success;
+      const double new_l_ij = Eq::limit(prm, b, U_i_new, new_p_ij, success);
+      lij_next[e] = (1. - old_l_ij) * new_l_ij;
+    }
+  }
+
+
+  /* Experimental alternative to k_high_order<Eq, false> (RJ_HO_EDGE=1).  A block of W warps owns
+   * one slice of 32 rows:
+   *   phase 1  every warp loads its columns' P_ij (k components) and symmetrised l_ij ONCE into
+   *            shared memory (MAXCOL * (k+1) * 32 doubles = 41.5 kB for 3D Euler);
+   *   phase 2  warp 0 forms U_i^{n+1} += (l_ij lambda) P_ij in COLUMN ORDER from shared memory --
+   *            the additions of the row-parallel kernel, bit for bit -- and publishes U_i^{n+1};
+   *   phase 3  every warp computes the next l_ij of its columns from the staged values.
+   * P_ij is read from global memory once instead of twice (1080 B/DoF of DRAM traffic, the
+   * difference between the measured 2937 and the algorithmic 1724 B/DoF of the row-parallel
+   * kernel), and 32 instead of 128 rows per block shrink the in-flight footprint. */
+  template <class Eq, int W, int MAXCOL>
+  __global__ void __launch_bounds__(32 * W, RJ_MB_HO_EDGE) k_high_order_edge(StencilView v,
+                                                                          typename Eq::Params prm,
+                                                                          uint32_t slice_begin,
+                                                                          uint32_t slice_end,
+                                                                          const double *__restrict__ bounds,
+                                                                          const double *__restrict__ pij,
+                                                                          const double *__restrict__ lij,
+                                                                          double *__restrict__ lij_next,
+                                                                          double *__restrict__ U_new)
+  {
+    constexpr int k = Eq::k, nb = Eq::n_bounds;
+    __shared__ double staged[MAXCOL * (k + 1) * 32]; /* [col][P_0..P_{k-1}, l][lane] */
+    __shared__ double updated[k * 32];               /* U_i^{n+1} of the slice's rows */
+    const uint32_t g = slice_begin + blockIdx.x;
+    if (g >= slice_end)
+      return; /* the whole block */
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t i = (g << 5) + lane;
+    const bool has_row = i < v.n_owned && v.row_length[i] > 1;
+    const uint32_t len = has_row ? v.row_length[i] : 0u;
+    const uint32_t base = v.slice_offsets[g] + lane;
+
+    for (uint32_t col = 1 + w; col < len; col += W) {
+      const uint32_t e = base + col * 32;
+      double *slot = staged + size_t(col) * (k + 1) * 32 + lane;
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        slot[q * 32] = pij[size_t(q) * v.E_owned + e];
+      slot[k * 32] = fmin(lij[e], lij[v.transposed[e]]);
+    }
+    __syncthreads();
+
+    if (w == 0 && has_row) {
+      double U_i_new[k];
+      load_state<k>(U_new, v.ld, i, U_i_new);
+      const double lambda = 1. / double(len - 1);
+      for (uint32_t col = 1; col < len; ++col) {
+        const double *slot = staged + size_t(col) * (k + 1) * 32 + lane;
+        const double ll = slot[k * 32] * lambda;
+#pragma unroll
+        for (int q = 0; q < k; ++q)
+          U_i_new[q] += ll * slot[q * 32];
+      }
+      store_state<k>(U_new, v.ld, i, U_i_new);
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        updated[q * 32 + lane] = U_i_new[q];
+    }
+    __syncthreads();
+
+    if (!has_row)
+      return;
+    double U_i_new[k], b[nb];
+#pragma unroll
+    for (int q = 0; q < k; ++q)
+      U_i_new[q] = updated[q * 32 + lane];
+    load_state<nb>(bounds, v.ld, i, b);
+    for (uint32_t col = 1 + w; col < len; col += W) {
+      const uint32_t e = base + col * 32;
+      const double *slot = staged + size_t(col) * (k + 1) * 32 + lane;
+      const double old_l_ij = slot[k * 32];
+      double new_p_ij[k];
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        new_p_ij[q] = (1. - old_l_ij) * slot[q * 32];
       bool success;
       const double new_l_ij = Eq::limit(prm, b, U_i_new, new_p_ij, success);
       lij_next[e] = (1. - old_l_ij) * new_l_ij;

@@ -736,7 +736,17 @@ namespace rjb
         sweep(
             [&](uint32_t b, uint32_t e) {
               tag(P_PIJ_LIJ);
+#if RJ_PIJ_EDGE
+              {
+                constexpr int W = RJ_PIJ_EDGE_W;
+                const uint32_t s0 = b / 32, s1 = (e + 31) / 32;
+                if (s1 > s0)
+                  launch(k_pij_lij_edge<Eq, W>, size_t(s1 - s0) * 32 * W, 32 * W, v, prm, s0, s1, new_state.U, r, bounds,
+                         scalars, pij, lij);
+              }
+#else
               launch_rows(k_pij_lij<Eq>, b, e, v, prm, b, e, new_state.U, r, bounds, scalars, pij, lij);
+#endif
             },
             [&] { exchange_matrix(lij); });
 
@@ -752,7 +762,16 @@ namespace rjb
           sweep(
               [&](uint32_t b, uint32_t e) {
                 tag(P_HIGH_ORDER_NEXT);
-                launch_rows(k_high_order<Eq, false>, b, e, v, prm, b, e, bounds, pij, lij, lij_next, new_state.U);
+#if RJ_HO_EDGE
+                if (max_row_length <= RJ_ALPHA_EDGE_MAXCOL) {
+                  constexpr int W = RJ_HO_EDGE_W;
+                  const uint32_t s0 = b / 32, s1 = (e + 31) / 32;
+                  if (s1 > s0)
+                    launch(k_high_order_edge<Eq, W, RJ_ALPHA_EDGE_MAXCOL>, size_t(s1 - s0) * 32 * W, 32 * W, v, prm, s0, s1,
+                           bounds, pij, lij, lij_next, new_state.U);
+                } else
+#endif
+                  launch_rows(k_high_order<Eq, false>, b, e, v, prm, b, e, bounds, pij, lij, lij_next, new_state.U);
               },
               [&] { exchange_matrix(lij_next); });
       }

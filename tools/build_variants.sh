@@ -18,6 +18,12 @@ alpha_edge:-DRJ_ALPHA_EDGE=1
 alpha_edge_w8:-DRJ_ALPHA_EDGE=1 -DRJ_ALPHA_EDGE_W=8 -DRJ_MB_ALPHA_EDGE=2
 alpha_edge_mb4:-DRJ_ALPHA_EDGE=1 -DRJ_MB_ALPHA_EDGE=4
 alpha_edge_prefetch:-DRJ_ALPHA_EDGE=1 -DRJ_PREFETCH_INDEX=1
+pij_edge:-DRJ_PIJ_EDGE=1
+pij_edge_w8:-DRJ_PIJ_EDGE=1 -DRJ_PIJ_EDGE_W=8 -DRJ_MB_PIJ_EDGE=2
+ho_edge:-DRJ_HO_EDGE=1
+ho_edge_mb4:-DRJ_HO_EDGE=1 -DRJ_MB_HO_EDGE=4
+edge_all:-DRJ_ALPHA_EDGE=1 -DRJ_PIJ_EDGE=1 -DRJ_HO_EDGE=1
+edge_all_prefetch:-DRJ_ALPHA_EDGE=1 -DRJ_PIJ_EDGE=1 -DRJ_HO_EDGE=1 -DRJ_PREFETCH_INDEX=1
 "}
 echo "$VARIANTS" | while IFS= read -r line; do
   [ -z "$line" ] && continue
