@@ -90,6 +90,22 @@ int rj_device_count(void);
 /* library version string */
 const char *rj_version(void);
 
+/* pow() of the path.  The reference routes every pow through ryujin::pow
+ * (source/simd.template.h:196-231), which is Agner Fog's VCL pow_template_d
+ * (simd-math/vectormath_exp.h:1508-1688).  The library is built with ONE implementation
+ * (csrc/Makefile: RJ_POW=vcl|vcl_fma|accurate); rj_pow_implementation() names it. */
+enum rj_pow_impl {
+  RJ_POW_ACCURATE = 0, /* accurate_pow.h: 0.50x ulp, ~libm rounding */
+  RJ_POW_VCL = 1,      /* vcl_pow.h: the reference's VCL pow, non-FMA form (default) */
+  RJ_POW_VCL_FMA = 2   /* vcl_pow.h: VCL as compiled on an FMA host */
+};
+int rj_pow_implementation(void);
+/* out[i] = pow(x[i], y[i]) with implementation `impl` (any of the three, independent of the
+ * build default), evaluated on the host (on_device = 0; works without a GPU: this is plain
+ * arithmetic, not a fallback of the sweep) or by a CUDA kernel (on_device = 1).  Test hook for
+ * tests/test_pow.py: device bits == host bits == reference VCL bits. */
+int rj_pow_evaluate(int impl, int on_device, size_t n, const double *x, const double *y, double *out);
+
 /* ------------------------------------------------------------------------ *
  * Offline data (replaces the read-only accessors of OfflineData,
  * source/offline_data.h:109-264, the SparsityPatternSIMD arrays,

@@ -812,6 +812,17 @@ void orc_offline_destroy(void *h) { delete static_cast<OfflineBase *>(h); }
   } while (0)
 
 /* sizes: out = (n_dofs, nnz, n_boundary, n_pairs) */
+/* owner rank of every row: N-rank emulation, see OfflineData::partition (orc_module.h) */
+void orc_offline_set_partition(void *h, const int *partition)
+{
+  WITH_OFFLINE(h, {
+    if (partition)
+      H.od.partition.assign(partition, partition + H.od.n_owned);
+    else
+      H.od.partition.clear();
+  });
+}
+
 void orc_offline_sizes(void *h, unsigned long long *out)
 {
   WITH_OFFLINE(h, {

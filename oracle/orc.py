@@ -145,6 +145,8 @@ class Oracle:
             path = vcl if os.path.exists(vcl) else port
         elif variant == "vcl":
             path = vcl
+        elif variant == "vcl_fma":
+            path = os.path.join(_HERE, "_ref", "liboracle_vcl_fma.so")
         elif variant == "port":
             path = port
         elif variant == "fma":
@@ -313,6 +315,16 @@ class Offline:
             self.o.lib.orc_offline_destroy(self.h)
         except Exception:
             pass
+
+    def set_partition(self, partition):
+        """owner rank of every row (N-rank emulation, orc_module.h OfflineData::partition); None
+        restores the single-rank semantics"""
+        if partition is None:
+            self.o.lib.orc_offline_set_partition(self.h, None)
+            return
+        p = np.ascontiguousarray(partition, dtype=np.int32)
+        assert len(p) == self.n
+        self.o.lib.orc_offline_set_partition(self.h, _ip(p))
 
     def arrays(self):
         if self._arrays is not None:

@@ -51,6 +51,19 @@ namespace orc
     double measure_of_omega = 0.;
     std::vector<BoundaryDescription<dim>> boundary_map;
     std::vector<CouplingDescription> coupling_boundary_pairs;
+    /* Optional: owner rank of every row.  Emulates an N-rank run of the reference inside one
+     * address space (tests of the multi-GPU path): with MPI every rank computes d_ij for ALL
+     * couplings to its ghost columns itself -- a ghost index is always larger than any owned
+     * index, so "j < i: skip and mirror" (hyperbolic_module.template.h:395-400, :461-476,
+     * :511-535) only ever applies to pairs owned by the same rank.  The caller supplies rows
+     * whose column order is the owner's local order, so row sums run in the rank's order. */
+    std::vector<int> partition;
+
+    /* true if entry (i, j) is filled from (j, i) instead of being computed by row i */
+    bool mirrored_from_upper(unsigned int i, unsigned int j) const
+    {
+      return j < i && (partition.empty() || partition[i] == partition[j]);
+    }
 
     unsigned int row_length(unsigned int i) const
     {
@@ -260,7 +273,7 @@ namespace orc
 
             if (col_idx == 0)
               continue;
-            if (j < i)
+            if (od_.mirrored_from_upper(i, j))
               continue;
 
             const double nrm = norm<dim>(c_ij);
@@ -284,7 +297,7 @@ namespace orc
         RiemannSolver riemann_solver(sys_);
         for (const auto &cp : od_.coupling_boundary_pairs) {
           const unsigned int i = cp.i, col_idx = cp.col_idx, j = cp.j;
-          if (j < i)
+          if (od_.mirrored_from_upper(i, j))
             continue;
           const auto U_i = get(old_U, i);
           const auto U_j = get(old_U, j);
@@ -314,7 +327,7 @@ namespace orc
           for (unsigned int col_idx = 1; col_idx < row_length; ++col_idx) {
             const std::size_t e = e0 + col_idx;
             const unsigned int j = od_.cols[e];
-            if (j < i)
+            if (od_.mirrored_from_upper(i, j))
               dij_[e] = dij_[od_.transposed[e]];
             d_sum -= dij_[e];
           }

@@ -159,6 +159,8 @@ _SIGNATURES = {
     "rj_last_error": (C.c_char_p, []),
     "rj_device_count": (C.c_int, []),
     "rj_version": (C.c_char_p, []),
+    "rj_pow_implementation": (C.c_int, []),
+    "rj_pow_evaluate": (C.c_int, [C.c_int, C.c_int, C.c_size_t, f64p, f64p, f64p]),
     "rj_offline_create": (C.c_int, [C.POINTER(vp), C.POINTER(OfflineDesc), C.c_int]),
     "rj_offline_destroy": (None, [vp]),
     "rj_offline_create_host_layout": (C.c_int, [C.POINTER(vp), C.POINTER(OfflineDesc)]),

@@ -5,6 +5,7 @@
 
 #include "../../include/ryujin_b200.h"
 #include "accurate_pow.h"
+#include "vcl_pow.h"
 
 #include <cfloat>
 #include <cstdint>
@@ -21,9 +22,32 @@
 #define RJ_LAUNCH_KERNEL(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #endif
 
+/* Which pow() the equation modules call (every pow of the path goes through path_pow):
+ *   1  vcl_pow<false>: the reference's own pow (Agner Fog's VCL as vendored under simd-math/,
+ *      called by ryujin::pow, source/simd.template.h:207-213) in its non-FMA form -- bit-identical
+ *      to oracle/_ref/liboracle_vcl.so, which compiles the reference's VCL sources.  DEFAULT: this
+ *      is what makes shock flows agree with the reference path to north_star's 1e-12.
+ *   2  vcl_pow<true>: VCL as it compiles on an FMA host (AVX2 / AVX-512 builds of the reference).
+ *   0  rj_pow (accurate_pow.h): 0.50x ulp table-driven pow, ~libm; faster, but not the
+ *      reference's rounding (kept as a build option: make RJ_POW=accurate). */
+#ifndef RJ_POW_IMPL
+#define RJ_POW_IMPL 1
+#endif
+
 namespace rjb
 {
   constexpr int warp_size = 32; /* slice height C of the sliced-ELL layout */
+
+  __device__ __forceinline__ double path_pow(const double x, const double y)
+  {
+#if RJ_POW_IMPL == 1
+    return vcl_pow<false>(x, y);
+#elif RJ_POW_IMPL == 2
+    return vcl_pow<true>(x, y);
+#else
+    return rj_pow(x, y);
+#endif
+  }
 
   RJ_DEVICE double positive_part(const double x)
   {

@@ -60,7 +60,7 @@ namespace rjb
     RJ_DEVICE static double specific_entropy(const Params &p, const double (&U)[k])
     {
       const double rho_inverse = 1. / U[0];
-      return internal_energy(U) * rj_pow(rho_inverse, p.gamma);
+      return internal_energy(U) * path_pow(rho_inverse, p.gamma);
     }
 
     RJ_DEVICE static double harten_entropy(const Params &p, const double (&U)[k])
@@ -70,7 +70,7 @@ namespace rjb
       for (int d = 1; d < dim; ++d)
         m2 += U[1 + d] * U[1 + d];
       const double rho_rho_e = U[0] * U[dim + 1] - 0.5 * m2;
-      return rj_pow(rho_rho_e, p.gamma_plus_one_inverse);
+      return path_pow(rho_rho_e, p.gamma_plus_one_inverse);
     }
 
     /* precomputation_loop body, hyperbolic_system.h:732-735 */
@@ -96,7 +96,7 @@ namespace rjb
         m2 += U[1 + d] * U[1 + d];
       const double rho_rho_e = U[0] * U[dim + 1] - 0.5 * m2;
       const double factor =
-          p.gamma_plus_one_inverse * rj_pow(rho_rho_e, -p.gamma * p.gamma_plus_one_inverse);
+          p.gamma_plus_one_inverse * path_pow(rho_rho_e, -p.gamma * p.gamma_plus_one_inverse);
       result[0] = factor * U[dim + 1];
 #pragma unroll
       for (int d = 0; d < dim; ++d)
@@ -214,7 +214,7 @@ namespace rjb
       const double R_2 = component == 2 ? vn_bar + 2. * a_bar / (gamma - 1.) : vn + 2. * a / (gamma - 1.);
 
       const double pr = pressure(p, U);
-      const double s = pr / rj_pow(rho, gamma);
+      const double s = pr / path_pow(rho, gamma);
 
       const double rho_inverse = 1. / rho; /* m / rho: Tensor / scalar multiplies by the inverse */
       double vperp[dim];
@@ -227,8 +227,8 @@ namespace rjb
       const double vn_new = 0.5 * (R_1 + R_2);
       const double tmp = ((gamma - 1.) / 4.) * (R_2 - R_1);
       double rho_new = 1. / (gamma * s) * (tmp * tmp);
-      rho_new = rj_pow(rho_new, 1. / (gamma - 1.));
-      const double p_new = s * rj_pow(rho_new, gamma);
+      rho_new = path_pow(rho_new, 1. / (gamma - 1.));
+      const double p_new = s * path_pow(rho_new, gamma);
 
       U_new[0] = rho_new;
 #pragma unroll
@@ -329,7 +329,7 @@ namespace rjb
       const double radicand = Az / (p_star + Bz);
       const double true_value = (p_star - rd.p) * sqrt(radicand);
       const double exponent = 0.5 * (gamma - 1.) / gamma;
-      const double factor = rj_pow(p_star / rd.p, exponent) - 1.;
+      const double factor = path_pow(p_star / rd.p, exponent) - 1.;
       const double false_value = 2. * rd.a * factor / (gamma - 1.);
       return p_star >= rd.p ? true_value : false_value;
     }
@@ -342,7 +342,7 @@ namespace rjb
       const double true_value =
           (denominator - 0.5 * (p_star - rd.p)) / (denominator * sqrt(radicand_inverse));
       const double exponent = (-1. - gamma) * 0.5 * p.gamma_inverse;
-      const double factor = (gamma - 1.) * 0.5 * p.gamma_inverse * rj_pow(p_star / rd.p, exponent) / rd.p;
+      const double factor = (gamma - 1.) * 0.5 * p.gamma_inverse * path_pow(p_star / rd.p, exponent) / rd.p;
       const double false_value = factor * 2. * rd.a * p.gamma_minus_one_inverse;
       return p_star >= rd.p ? true_value : false_value;
     }
@@ -379,9 +379,9 @@ namespace rjb
         const double factor = (gamma - 1.) * 0.5;
         const double numerator = positive_part(rd_i.a + rd_j.a - factor * (rd_j.u - rd_i.u));
         const double denominator =
-            rd_i.a * rj_pow(rd_i.p * inv_p_j, -factor * p.gamma_inverse) + rd_j.a;
+            rd_i.a * path_pow(rd_i.p * inv_p_j, -factor * p.gamma_inverse) + rd_j.a;
         const double exponent = 2.0 * gamma * p.gamma_minus_one_inverse;
-        rarefaction = rd_j.p * rj_pow(numerator / denominator, exponent);
+        rarefaction = rd_j.p * path_pow(numerator / denominator, exponent);
       }
 
       /* p_star_failsafe, :332-374; radicand_inverse terms shared with
@@ -622,7 +622,7 @@ namespace rjb
         for (int q = 0; q < k; ++q)
           U_r[q] = U[q] + t_r * P[q];
         const double rho_r = U_r[0];
-        const double rho_r_gamma = rj_pow(rho_r, gamma);
+        const double rho_r_gamma = path_pow(rho_r, gamma);
         const double rho_e_r = internal_energy(U_r);
         const double psi_r = relax_small * rho_r * rho_e_r - s_min * rho_r * rho_r_gamma;
 
@@ -635,7 +635,7 @@ namespace rjb
         for (int q = 0; q < k; ++q)
           U_l[q] = U[q] + t_l * P[q];
         const double rho_l = U_l[0];
-        const double rho_l_gamma = rj_pow(rho_l, gamma);
+        const double rho_l_gamma = path_pow(rho_l, gamma);
         const double rho_e_l = internal_energy(U_l);
         const double psi_l = relax_small * rho_l * rho_e_l - s_min * rho_l * rho_l_gamma;
 
@@ -714,8 +714,8 @@ namespace rjb
         const double T = 1. - (gamma - 1.) / (2. * gamma) * factor * factor;
         const double u = iv.mach_number - factor * pb1;
         const double v = factor * pb0;
-        const double rho = rj_pow(T, 1. / (gamma - 1.));
-        const double pr = rj_pow(rho, gamma);
+        const double rho = path_pow(T, 1. / (gamma - 1.));
+        const double pr = path_pow(rho, gamma);
         const double E = pr / (gamma - 1.) + 0.5 * rho * (u * u + v * v);
 #pragma unroll
         for (int q = 0; q < k; ++q)

@@ -1085,6 +1085,28 @@ namespace rjb
 } // namespace rjb
 
 
+namespace rjb
+{
+  template <int impl>
+  __host__ __device__ inline double pow_by_impl(double x, double y)
+  {
+    if (impl == RJ_POW_VCL)
+      return vcl_pow<false>(x, y);
+    if (impl == RJ_POW_VCL_FMA)
+      return vcl_pow<true>(x, y);
+    return rj_pow(x, y);
+  }
+
+  template <int impl>
+  __global__ void k_pow_evaluate(size_t n, const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ out)
+  {
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t < n)
+      out[t] = pow_by_impl<impl>(x[t], y[t]);
+  }
+} // namespace rjb
+
+
 /* ======================================================================== *
  *                              extern "C"
  * ======================================================================== */
@@ -1103,7 +1125,49 @@ int rj_device_count(void)
   return n;
 }
 
-const char *rj_version(void) { return "ryujin_b200 0.1 (sm_100a)"; }
+const char *rj_version(void) { return "ryujin_b200 0.2 (sm_100a)"; }
+
+int rj_pow_implementation(void) { return RJ_POW_IMPL; }
+
+
+int rj_pow_evaluate(int impl, int on_device, size_t n, const double *x, const double *y, double *out)
+{
+  return guarded([&] {
+    if (impl < 0 || impl > 2 || (n && (!x || !y || !out)))
+      throw InvalidArgument("rj_pow_evaluate: invalid argument");
+    if (!on_device) {
+      for (size_t t = 0; t < n; ++t)
+        out[t] = impl == RJ_POW_VCL ? pow_by_impl<RJ_POW_VCL>(x[t], y[t])
+                                    : impl == RJ_POW_VCL_FMA ? pow_by_impl<RJ_POW_VCL_FMA>(x[t], y[t])
+                                                             : pow_by_impl<RJ_POW_ACCURATE>(x[t], y[t]);
+      return RJ_OK;
+    }
+    if (rj_device_count() == 0)
+      throw NoDevice("rj_pow_evaluate: no CUDA device");
+    double *d = nullptr;
+    RJ_CUDA(cudaMalloc(&d, 3 * n * sizeof(double) + 8));
+    try {
+      RJ_CUDA(cudaMemcpy(d, x, n * sizeof(double), cudaMemcpyHostToDevice));
+      RJ_CUDA(cudaMemcpy(d + n, y, n * sizeof(double), cudaMemcpyHostToDevice));
+      const unsigned grid = unsigned((n + 255) / 256);
+      if (n) {
+        if (impl == RJ_POW_VCL)
+          RJ_LAUNCH_KERNEL(k_pow_evaluate<RJ_POW_VCL>, grid, 256, 0, n, d, d + n, d + 2 * n);
+        else if (impl == RJ_POW_VCL_FMA)
+          RJ_LAUNCH_KERNEL(k_pow_evaluate<RJ_POW_VCL_FMA>, grid, 256, 0, n, d, d + n, d + 2 * n);
+        else
+          RJ_LAUNCH_KERNEL(k_pow_evaluate<RJ_POW_ACCURATE>, grid, 256, 0, n, d, d + n, d + 2 * n);
+      }
+      RJ_CUDA(cudaGetLastError());
+      RJ_CUDA(cudaMemcpy(out, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+    } catch (...) {
+      cudaFree(d);
+      throw;
+    }
+    RJ_CUDA(cudaFree(d));
+    return RJ_OK;
+  });
+}
 
 int rj_offline_create(rj_offline **out, const rj_offline_desc *desc, int device)
 {

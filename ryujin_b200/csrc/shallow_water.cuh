@@ -111,7 +111,7 @@ namespace rjb
     RJ_DEVICE static void precompute(const Params &p, const double (&U)[k], double (&prec)[n_prec])
     {
       prec[0] = mathematical_entropy(p, U);
-      prec[1] = rj_pow(water_depth_sharp(p, U), 4. / 3.);
+      prec[1] = path_pow(water_depth_sharp(p, U), 4. / 3.);
     }
 
     /* element (comp, d) of f(U) (with_pressure) or g(U), hyperbolic_system.h:1022-1056 */

@@ -9,9 +9,9 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 import ryujin_b200 as rj
 from oracle import orc
-from helpers import oracle_offline_from_host, rel_linf, rel_linf_per_component
+from helpers import matching_oracle, oracle_offline_from_host, rel_linf, rel_linf_per_component
 
-oracle = orc.Oracle("port")
+oracle = matching_oracle()[0]  # the oracle build with the pow the product was built for
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 B = rj.Boundary
 ids_pool = [B.slip, B.dirichlet, B.do_nothing, B.no_slip, B.dynamic]

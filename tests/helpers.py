@@ -7,6 +7,35 @@ from oracle import orc
 
 B_DIRICHLET, B_SLIP, B_DO_NOTHING = 4, 2, 0
 
+POW_IMPL_NAMES = {0: "accurate", 1: "vcl", 2: "vcl_fma"}
+
+
+def product_pow_impl():
+    """which pow() the loaded product library was built with (rj_pow_implementation)"""
+    import ryujin_b200 as rj
+
+    return int(rj.lib.rj_pow_implementation())
+
+
+def matching_oracle():
+    """The oracle build whose pow() is the one the product library was built for:
+      vcl      -> oracle/_ref/liboracle_vcl.so      (the reference's own VCL sources, non-FMA form;
+                  shares no pow code with the product -- this is the independent parity target)
+      vcl_fma  -> oracle/_ref/liboracle_vcl_fma.so  (VCL as it compiles on an FMA host)
+      accurate -> oracle/liboracle.so               (libm pow; parity only up to pow rounding)
+    -> (oracle, exact) where `exact` says that every operation of the path, pow included, is
+    the same IEEE operation on both sides, i.e. that north_star's 1e-12 must hold outright."""
+    impl = product_pow_impl()
+    if impl == 1:
+        o = orc.Oracle("vcl")
+        assert o.lib.orc_uses_vcl(), "oracle/_ref/liboracle_vcl.so is not a VCL build"
+        return o, True
+    if impl == 2:
+        o = orc.Oracle("vcl_fma")
+        assert o.lib.orc_uses_vcl()
+        return o, True
+    return orc.Oracle("port"), False
+
 
 def oracle_offline_from_host(oracle, host):
     """Feed the product generator's arrays (local numbering) to the oracle."""
@@ -84,10 +113,11 @@ def make_product(case, n_cells, device=0, comm=None, rank=0, n_ranks=1, module_p
     return od, module
 
 
-def make_oracle(oracle, case, host, **prm):
-    """-> (offline, sim) of the oracle on the product's arrays"""
+def make_oracle(oracle, case, host, off=None, **prm):
+    """-> (offline, sim) of the oracle on the product's arrays (or on a prepared Offline `off`)"""
     c = CASES[case]
-    off = oracle_offline_from_host(oracle, host)
+    if off is None:
+        off = oracle_offline_from_host(oracle, host)
     iv = c["iv"]
     sim = off.euler_sim(
         kind=KIND_ORACLE[iv["kind"]],
@@ -265,9 +295,10 @@ def make_sw_product(case, n_cells, device=0, comm=None, rank=0, n_ranks=1, **mp_
     return od, module
 
 
-def make_sw_oracle(oracle, case, host, **prm_extra):
+def make_sw_oracle(oracle, case, host, off=None, **prm_extra):
     c = SW_CASES[case]
-    off = oracle_offline_from_host(oracle, host)
+    if off is None:
+        off = oracle_offline_from_host(oracle, host)
     iv = c["iv"]
     prm = dict(c["eq"])
     prm.update(c["mp"])
@@ -306,3 +337,63 @@ CASES.update({
         iv=dict(kind="uniform", direction=[1.0, 0.3], position=[0.0, 0.0], primitive=[1.4, 3.0, 1.0]),
     ),
 })
+
+
+# ---------------------------------------------------------------------------------------
+# N-rank runs against the oracle: the reference's result depends on the partition at
+# round-off level -- every rank computes d_ij towards its ghost columns itself and sums its rows in
+# its LOCAL column order (ghost columns last).  The oracle reproduces an N-rank run bit for bit
+# inside one address space when it is handed (a) the concatenation of the ranks' local stencils,
+# rows and columns in each owner's local order, and (b) the owner rank of every row
+# (orc_module.h: OfflineData::partition).
+def merged_partition_stencil(mesh, n_ranks):
+    """-> dict of arrays of the concatenated per-rank stencils (numbering G = rank offset + local
+    owned index) + 'partition' + 'hosts' + 'offsets'"""
+    import ryujin_b200 as rj
+
+    hosts = [rj.HostOfflineData(mesh, r, n_ranks) for r in range(n_ranks)]
+    offsets = np.concatenate([[0], np.cumsum([h.n_owned for h in hosts])]).astype(np.int64)
+    n_global = int(offsets[-1])
+    assert n_global == hosts[0].n_global_dofs
+    G_of_mesh_global = np.full(n_global, -1, dtype=np.int64)
+    for r, h in enumerate(hosts):
+        G_of_mesh_global[h.global_index[: h.n_owned].astype(np.int64)] = offsets[r] + np.arange(h.n_owned)
+    assert (G_of_mesh_global >= 0).all()
+    row_starts, cols, mij, cij, mi, b_dof, b_normal, b_id, b_pos, pairs, part = [np.zeros(1, dtype=np.int64)], [], [], [], [], [], [], [], [], [], []
+    nnz0 = 0
+    for r, h in enumerate(hosts):
+        local_to_G = G_of_mesh_global[h.global_index.astype(np.int64)]  # owned and ghost rows
+        assert np.array_equal(local_to_G[: h.n_owned], offsets[r] + np.arange(h.n_owned))
+        row_starts.append(h.row_starts[1:].astype(np.int64) + nnz0)
+        nnz0 += h.nnz
+        cols.append(local_to_G[h.cols.astype(np.int64)])
+        mij.append(h.mij)
+        cij.append(h.cij)
+        mi.append(h.mi[: h.n_owned])
+        b_dof.append(h.boundary_dof.astype(np.int64) + offsets[r])
+        b_normal.append(h.boundary_normal)
+        b_id.append(h.boundary_id)
+        b_pos.append(h.boundary_position)
+        if len(h.coupling_pairs):
+            p = h.coupling_pairs.astype(np.int64)
+            pairs.append(np.stack([p[:, 0] + offsets[r], p[:, 1], local_to_G[p[:, 2]]], axis=1))
+        part.append(np.full(h.n_owned, r, dtype=np.int32))
+    return dict(
+        dim=hosts[0].dim, hosts=hosts, offsets=offsets,
+        row_starts=np.concatenate(row_starts).astype(np.uint32), cols=np.concatenate(cols).astype(np.uint32),
+        mij=np.concatenate(mij), cij=np.concatenate(cij), mi=np.concatenate(mi),
+        measure_of_omega=hosts[0].measure_of_omega,
+        boundary_dof=np.concatenate(b_dof).astype(np.uint32), boundary_normal=np.concatenate(b_normal),
+        boundary_id=np.concatenate(b_id).astype(np.int32), boundary_position=np.concatenate(b_pos),
+        coupling_pairs=(np.concatenate(pairs) if pairs else np.zeros((0, 3))).astype(np.uint32),
+        partition=np.concatenate(part), positions=np.concatenate([h.positions for h in hosts]),
+    )
+
+
+def oracle_offline_from_partition(oracle, merged):
+    m = merged
+    off = oracle.offline_from_arrays(m["dim"], m["row_starts"], m["cols"], m["mij"], m["cij"], m["mi"], m["measure_of_omega"],
+                                     m["boundary_dof"], m["boundary_normal"], m["boundary_id"], m["boundary_position"],
+                                     m["coupling_pairs"].ravel())
+    off.set_partition(m["partition"])
+    return off

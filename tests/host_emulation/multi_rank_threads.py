@@ -18,7 +18,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import ryujin_b200 as rj  # noqa: E402
-from helpers import CASES, SW_CASES, make_mesh, make_sw_product, rel_linf, sw_bathymetry  # noqa: E402
+from helpers import (CASES, SW_CASES, make_mesh, make_oracle, make_sw_oracle, make_sw_product, matching_oracle,  # noqa: E402
+                     merged_partition_stencil, oracle_offline_from_partition, rel_linf, sw_bathymetry)
 
 
 def build(case, n_cells, rank, world, comm):
@@ -40,6 +41,7 @@ def run_rank(case, n_cells, cycles, rank, world, uid, out, ti_kw):
         ti = rj.TimeIntegrator(module, rj.TimeSteppingScheme.erk_33, **ti_kw)
         state = module.state_vector()
         state.interpolate(0.0)
+        U0 = state.download()
         t, taus = 0.0, []
         for _ in range(cycles):
             tau = ti.step(state, t)
@@ -47,7 +49,7 @@ def run_rank(case, n_cells, cycles, rank, world, uid, out, ti_kw):
             t += tau
         host = od.host
         out[rank] = (host.global_index[: host.n_owned].astype(np.int64), state.download(), np.array(taus),
-                     (module.n_restarts(), module.n_warnings()), int(host.n_global_dofs))
+                     (module.n_restarts(), module.n_warnings()), int(host.n_global_dofs), U0)
     except BaseException as e:  # noqa: BLE001 -- reported in the main thread
         out[rank] = e
 
@@ -67,12 +69,41 @@ def run(case, n_cells, cycles, world, **ti_kw):
             raise RuntimeError("rank %d did not finish" % r)
     n_global = out[0][4]
     full = np.zeros((n_global, out[0][1].shape[1]))
-    for idx, U, _, _, _ in out:
+    for idx, U, _, _, _, _ in out:
         full[idx] = U
     for o in out[1:]:
         assert np.array_equal(o[2], out[0][2]), "ranks disagree on tau"
         assert o[3] == out[0][3], "ranks disagree on the restart / warning counters"
+    run.last_rank_order = (np.concatenate([o[1] for o in out]), np.concatenate([o[5] for o in out]))
     return full, out[0][2], out[0][3]
+
+
+def oracle_n_ranks(oracle, case, n_cells, cycles, world, U0, ti_kw):
+    """the same N-rank run inside the oracle (helpers.merged_partition_stencil): rows and columns in
+    every owner's local order, d_ij towards ghost columns computed by each owner -- the reference's
+    MPI semantics, so the comparison is at north_star's tolerance, not at partition round-off"""
+    if case in SW_CASES:
+        mesh = rj.CartesianMesh.rectangular_domain(SW_CASES[case]["bottom_left"], SW_CASES[case]["top_right"], n_cells,
+                                                   SW_CASES[case]["boundary"])
+    else:
+        mesh = make_mesh(case, n_cells)
+    merged = merged_partition_stencil(mesh, world)
+    off = oracle_offline_from_partition(oracle, merged)
+    if case in SW_CASES:
+        _, sim = make_sw_oracle(oracle, case, None, off=off)
+        z = np.concatenate([sw_bathymetry(h) for h in merged["hosts"]])
+        sim.set_initial_precomputed(z)
+    else:
+        _, sim = make_oracle(oracle, case, None, off=off)
+    recovery = "none" if ti_kw.get("cfl_recovery_strategy") == rj.CFLRecoveryStrategy.none else "bang bang control"
+    sim.configure_time_integrator("erk 33", ti_kw.get("cfl_min", 0.45), ti_kw.get("cfl_max", 0.9), recovery)
+    sim.set_U(U0, 0)
+    t, taus = 0.0, []
+    for _ in range(cycles):
+        tau = sim.time_step(t)
+        taus.append(tau)
+        t += tau
+    return sim.get_U(0), np.array(taus), sim.counters()
 
 
 def main():
@@ -90,12 +121,23 @@ def main():
         os.environ["RYUJIN_B200_OVERLAP"] = "0"
         U_serial, taus_serial, counters_serial = run(case, n_cells, cycles, world, **kw)
         same = np.array_equal(U, U_serial) and np.array_equal(taus, taus_serial) and counters == counters_serial
+        U_ranks, U0_ranks = run.last_rank_order
         U1, taus1, counters1 = run(case, n_cells, cycles, 1, **kw)
         err = rel_linf(U, U1)
         dtau = float(np.max(np.abs(taus - taus1) / taus1))
         print("%s %s x%d ranks, %d cycles: vs single rank %.3e (tau %.2e), overlap on/off bit-identical %s, counters %s"
               % (case, n_cells, world, cycles, err, dtau, same, counters == counters1), flush=True)
         ok = ok and same and err < tol and dtau < max(tol, 1e-12) and counters == counters1
+        # against the oracle running the same partition: north_star's tolerance
+        oracle, exact = matching_oracle()
+        U_orc, taus_orc, counters_orc = oracle_n_ranks(oracle, case, n_cells, cycles, world, U0_ranks, kw)
+        err_o = rel_linf(U_ranks, U_orc)
+        dtau_o = float(np.max(np.abs(taus - taus_orc) / taus_orc))
+        print("%s x%d ranks vs oracle with the same partition: rel Linf %.3e, tau %.2e, bit-identical %s, counters %s"
+              % (case, world, err_o, dtau_o, bool(np.array_equal(U_ranks, U_orc.reshape(U_ranks.shape))), counters == counters_orc),
+              flush=True)
+        if exact:
+            ok = ok and err_o <= 1e-12 and dtau_o <= 1e-13 and counters == counters_orc
     print("multi-rank parity ok" if ok else "multi-rank parity FAILED")
     return 0 if ok else 1
 

@@ -4,9 +4,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port 29511 tests/multi_gpu_parity.py
 
-Every rank owns a z-slab (y-slab in 2D) of the same global mesh; ghost values travel over
-NCCL (C1-C9 of SURVEY.md 2b).  Rank 0 additionally runs the whole mesh on its own GPU and
-compares the gathered multi-rank state with it.  As in the reference (mpirun=4 vs mpirun=8
+Every rank owns a block of the same global mesh; ghost values travel over NCCL (C1-C9 of
+SURVEY.md 2b).  Rank 0 runs the CPU oracle on the same partition (helpers.merged_partition_stencil:
+north_star's 1e-12 against the reference semantics of an N-rank run) and additionally the whole
+mesh on its own GPU (partition round-off).  As in the reference (mpirun=4 vs mpirun=8
 goldens) the result depends on the partition at round-off level only: d_ij across a rank
 boundary is computed by each owner in its own operand order
 (hyperbolic_module.template.h:334-337).
@@ -23,7 +24,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import ryujin_b200 as rj  # noqa: E402
-from helpers import CASES, SW_CASES, make_mesh, make_sw_product, rel_linf, sw_bathymetry  # noqa: E402
+from helpers import (CASES, SW_CASES, make_mesh, make_oracle, make_sw_oracle, make_sw_product, matching_oracle,  # noqa: E402
+                     merged_partition_stencil, oracle_offline_from_partition, rel_linf, sw_bathymetry)
 
 
 def run(case, n_cells, cycles, rank, world, comm, device, stepping=None, **ti_kw):
@@ -43,12 +45,41 @@ def run(case, n_cells, cycles, rank, world, comm, device, stepping=None, **ti_kw
         ti.stepping = stepping
     state = module.state_vector()
     state.interpolate(0.0)
+    run.U0 = state.download()
     t, taus = 0.0, []
     for _ in range(cycles):
         tau = ti.step(state, t)
         taus.append(tau)
         t += tau
     return od, module, state.download(), np.array(taus)
+
+
+def oracle_n_ranks(oracle, case, n_cells, cycles, world, U0, ti_kw):
+    """the same N-rank run inside the oracle (helpers.merged_partition_stencil): rows and columns in
+    every owner's local order, d_ij towards ghost columns computed by each owner -- the reference's
+    MPI semantics -- so multi-GPU parity is measured at north_star's tolerance against the oracle, not
+    at partition round-off against another run of the product"""
+    if case in SW_CASES:
+        c = SW_CASES[case]
+        mesh = rj.CartesianMesh.rectangular_domain(c["bottom_left"], c["top_right"], n_cells, c["boundary"])
+    else:
+        mesh = make_mesh(case, n_cells)
+    merged = merged_partition_stencil(mesh, world)
+    off = oracle_offline_from_partition(oracle, merged)
+    if case in SW_CASES:
+        _, sim = make_sw_oracle(oracle, case, None, off=off)
+        sim.set_initial_precomputed(np.concatenate([sw_bathymetry(h) for h in merged["hosts"]]))
+    else:
+        _, sim = make_oracle(oracle, case, None, off=off)
+    recovery = "none" if ti_kw.get("cfl_recovery_strategy") == rj.CFLRecoveryStrategy.none else "bang bang control"
+    sim.configure_time_integrator("erk 33", ti_kw.get("cfl_min", 0.45), ti_kw.get("cfl_max", 0.9), recovery)
+    sim.set_U(U0, 0)
+    t, taus = 0.0, []
+    for _ in range(cycles):
+        tau = sim.time_step(t)
+        taus.append(tau)
+        t += tau
+    return sim.get_U(0), np.array(taus), sim.counters()
 
 
 def main():
@@ -67,6 +98,7 @@ def main():
         ("sw_vortex2d", [32, 16 * world], 10, dict(cfl_min=0.25, cfl_max=0.25, cfl_recovery_strategy=rj.CFLRecoveryStrategy.none), 2e-10),
     ):
         od, module, U, taus = run(case, n_cells, cycles, rank, world, comm, local, **kw)
+        U0 = run.U0
         # the three ways of driving a cycle (host round trips / device-resident / CUDA graph with
         # the NCCL exchanges captured) must agree bitwise on every rank
         for mode in (rj.Stepping.host, rj.Stepping.graph):
@@ -84,6 +116,23 @@ def main():
         full[idx] = torch.from_numpy(U).cuda()
         dist.all_reduce(full)  # disjoint ownership: sum == gather
         counters = torch.tensor([module.n_restarts(), module.n_warnings()], device="cuda")
+        # rank-ordered concatenation of the owned rows (the numbering of the partition oracle)
+        pieces = [None] * world
+        dist.all_gather_object(pieces, (U, U0))
+        if rank == 0:
+            oracle, exact = matching_oracle()
+            U_ranks = np.concatenate([p[0] for p in pieces])
+            U0_ranks = np.concatenate([p[1] for p in pieces])
+            U_orc, taus_orc, counters_orc = oracle_n_ranks(oracle, case, n_cells, cycles, world, U0_ranks, kw)
+            err_o = rel_linf(U_ranks, U_orc)
+            dtau_o = float(np.max(np.abs(taus - taus_orc) / taus_orc))
+            same_o = counters_orc == tuple(int(x) for x in counters.tolist())
+            print("multi-gpu %s %s x%d ranks, %d cycles vs ORACLE with the same partition: rel Linf %.3e, tau %.2e, "
+                  "bit-identical %s, counters equal %s"
+                  % (case, n_cells, world, cycles, err_o, dtau_o, bool(np.array_equal(U_ranks, U_orc.reshape(U_ranks.shape))), same_o),
+                  flush=True)
+            if exact:
+                ok = ok and err_o <= 1e-12 and dtau_o <= 1e-13 and same_o
         if rank == 0:
             od1, module1, U1, taus1 = run(case, n_cells, cycles, 0, 1, None, local, **kw)
             g1 = od1.host.global_index[: od1.host.n_owned].astype(np.int64)

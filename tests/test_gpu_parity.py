@@ -8,19 +8,25 @@ import numpy as np
 import pytest
 
 from conftest import load_golden
-from helpers import CASES, initial_state_host, make_mesh, make_oracle, make_product, rel_linf, rel_linf_per_component
+from helpers import (CASES, initial_state_host, make_mesh, make_oracle, make_product, matching_oracle, rel_linf,
+                     rel_linf_per_component)
 
 pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
-def oracle(oracle_port):
-    """GPU parity is measured against the oracle built with a (nearly) correctly rounded pow
-    (libm, 0.50x ulp), which is what the device's rj_pow reproduces in 99.97% of all calls.
-    The reference's own pow (Agner Fog's VCL) is only accurate to ~1.8 ulp and differs between
-    ISAs (tests/euler/*.output.{sse2,avx2,avx512}), so "the reference" is itself a family of
-    results; test_reference_pow_family bounds its spread with the VCL build of the oracle."""
-    return oracle_port
+def oracle():
+    """The parity target: the oracle build whose pow() is the one the product was built for
+    (helpers.matching_oracle).  With the default build that is oracle/_ref/liboracle_vcl.so -- the
+    CPU restatement linked against the reference's OWN pow (Agner Fog's VCL, compiled from the
+    reference tree); the product reaches the same bits with its device restatement of that
+    algorithm (csrc/vcl_pow.h), so nothing of the product is inside the oracle."""
+    return matching_oracle()[0]
+
+
+@pytest.fixture(scope="module")
+def exact_pow():
+    return matching_oracle()[1]
 
 
 def gpu_and_oracle(oracle, case, n_cells, **prm):
@@ -182,113 +188,86 @@ def run_cycles(module, sims, n_cycles, scheme_name, cfl_min=0.45, cfl_max=0.9, r
 
 
 def family_report(label, state, taus, sims, taus_refs):
-    """Deviations GPU <-> oracle(libm pow) <-> oracle(VCL pow)."""
+    """Deviations GPU <-> parity target (sims[0]) and, for information, <-> a second CPU build of the
+    same restatement with another pow (sims[1], libm): the spread of the reference path itself."""
     U = state.download()
-    U_port = sims[0].get_U(0)
-    rep = dict(gpu_port=rel_linf(U, U_port), tau_gpu_port=float(np.max(np.abs(taus - taus_refs[0]) / taus_refs[0])))
+    U_ref = sims[0].get_U(0)
+    rep = dict(gpu_ref=rel_linf(U, U_ref), tau_gpu_ref=float(np.max(np.abs(taus - taus_refs[0]) / taus_refs[0])),
+               bit_identical=bool(np.array_equal(U, U_ref.reshape(U.shape))))
     if len(sims) > 1:
-        U_vcl = sims[1].get_U(0)
-        rep.update(port_vcl=rel_linf(U_port, U_vcl), gpu_vcl=rel_linf(U, U_vcl),
-                   tau_port_vcl=float(np.max(np.abs(taus_refs[0] - taus_refs[1]) / taus_refs[1])))
-    print(label + ": " + "  ".join("%s %.2e" % kv for kv in sorted(rep.items())))
+        U_alt = sims[1].get_U(0)
+        rep.update(ref_alt=rel_linf(U_ref, U_alt), gpu_alt=rel_linf(U, U_alt),
+                   tau_ref_alt=float(np.max(np.abs(taus_refs[0] - taus_refs[1]) / taus_refs[1])))
+    print(label + ": " + "  ".join("%s %s" % (k, ("%.2e" % v) if isinstance(v, float) else v) for k, v in sorted(rep.items())))
     return rep
 
 
-def assert_within_reference_family(rep, floor=1e-12, tau_floor=1e-13, factor=4.0, hard_limit=1e-7):
+def assert_parity(rep, exact, floor=1e-12, tau_floor=1e-13, factor=4.0, hard_limit=1e-7):
     """Parity criterion for multi-step runs.
 
-    A smooth flow reproduces the oracle to ~1e-14.  On flows with shocks the reference
-    algorithm amplifies a one-ulp difference in a single pow() to ~1e-10 within 20 cycles
-    (two CPU builds of the reference path that differ only in the pow implementation --
-    libm vs the reference's own VCL -- deviate by 5.8e-10; the reference ships per-ISA goldens
-    for the same reason).  The CUDA path is therefore required to stay (a) within `floor`
-    of the oracle, or (b) no further from it than `factor` x the spread between the two
-    reference builds, and always (c) below a hard limit that a real defect would exceed."""
-    assert rep["gpu_port"] < hard_limit
-    spread = rep.get("port_vcl")
-    if spread is None:
-        assert rep["gpu_port"] < 1e-9
+    exact (the default build: product pow == the reference's VCL pow == the oracle's pow): north_star's
+    tolerance holds outright -- state within 1e-12 relative L-infinity, tau sequence within 1e-13,
+    shock flows included.
+
+    not exact (RJ_POW=accurate builds, compared with the libm oracle): a shock flow amplifies a
+    one-ulp difference in a single pow() to ~1e-10 within 20 cycles (two CPU builds of the reference
+    path that differ only in pow deviate by 5.8e-10), so the CUDA path must stay within `factor` x
+    the spread between two CPU builds, and below a hard limit that a real defect would exceed."""
+    if exact:
+        assert rep["gpu_ref"] <= floor and rep["tau_gpu_ref"] <= tau_floor, rep
         return
-    assert rep["gpu_port"] <= max(factor * spread, floor), rep
-    assert rep["tau_gpu_port"] <= max(factor * rep["tau_port_vcl"], tau_floor), rep
-    assert rep["gpu_vcl"] <= max(factor * spread, floor), rep
+    assert rep["gpu_ref"] < hard_limit
+    spread = rep.get("ref_alt")
+    if spread is None:
+        assert rep["gpu_ref"] < 1e-9
+        return
+    assert rep["gpu_ref"] <= max(factor * spread, floor), rep
+    assert rep["tau_gpu_ref"] <= max(factor * rep["tau_ref_alt"], tau_floor), rep
 
 
 @pytest.fixture(scope="module")
-def oracle_vcl():
-    from oracle import orc
-
-    try:
-        o = orc.Oracle("vcl")
-    except OSError:
-        return None
-    return o if o.lib.orc_uses_vcl() else None
+def oracle_alt(oracle, oracle_port):
+    """a second CPU build of the restatement with another pow (libm), to report the reference
+    path's own spread next to the GPU deviation; None when the parity target already is that build"""
+    return None if oracle.path == oracle_port.path else oracle_port
 
 
-@pytest.fixture(scope="module")
-def oracle_rjpow():
-    """the restatement built with the product's own pow (oracle/liboracle_rjpow.so): every other
-    operation of the path is IEEE +, -, *, /, sqrt in the reference's order on both sides, so the
-    CUDA path has to reproduce this build to the last bit -- which isolates pow() rounding as the
-    only source of the deviations from the libm and VCL builds"""
-    from oracle import orc
-
-    return orc.Oracle("rjpow")
-
-
-def assert_north_star_tolerance(label, module, state, taus, sim, taus_ref):
-    """north_star: state within 1e-12 relative L-infinity, tau sequence within 1e-13"""
-    U, U_ref = state.download(), sim.get_U(0).reshape(state.download().shape)
-    err = rel_linf(U, U_ref)
-    dtau = float(np.max(np.abs(taus - taus_ref) / taus_ref))
-    print("%s vs oracle(rj_pow): rel Linf %.3e, tau %.2e, bit-identical %s" % (label, err, dtau, bool(np.array_equal(U, U_ref))))
-    assert err <= 1e-12 and dtau <= 1e-13
-    assert (module.n_restarts(), module.n_warnings()) == sim.counters()
-
-
-def both(oracle, oracle_vcl, case, host, **prm):
+def both(oracle, oracle_alt, case, host, **prm):
     sims = [make_oracle(oracle, case, host, **prm)[1]]
-    if oracle_vcl is not None:
-        sims.append(make_oracle(oracle_vcl, case, host, **prm)[1])
+    if oracle_alt is not None:
+        sims.append(make_oracle(oracle_alt, case, host, **prm)[1])
     return sims
 
 
-def test_config1_sod_2d_256x256_100_cycles(oracle, oracle_vcl, oracle_rjpow):
+def test_config1_sod_2d_256x256_100_cycles(oracle, oracle_alt, exact_pow):
     """BASELINE config 1: 2D Euler Sod shock tube, 256x256, 100 ERK33 cycles (= 300 forward
-    Euler updates).  Against the restatement with the same pow the north_star tolerance (1e-12)
-    holds -- the states are bit-identical; against the libm and VCL builds the deviation is that
-    of the two CPU builds from each other (pow rounding amplified by the shock)."""
+    Euler updates) against the oracle linked with the reference's own pow: north_star's tolerance
+    (state 1e-12, tau 1e-13) through the shock; identical restart / warning counters."""
     od, module = make_product("sod2d", [256, 256])
     assert od.host.n_owned == 257 * 257
-    sims = both(oracle, oracle_vcl, "sod2d", od.host)
-    sims.append(make_oracle(oracle_rjpow, "sod2d", od.host)[1])
+    sims = both(oracle, oracle_alt, "sod2d", od.host)
     state, taus, refs = run_cycles(module, sims, 100, "erk 33")
-    assert_north_star_tolerance("config1 sod2d 256x256, 100 cycles", module, state, taus, sims[-1], refs[-1])
-    rep = family_report("config1 sod2d 256x256, 100 cycles", state, taus, sims[:-1], refs[:-1])
-    assert_within_reference_family(rep)
+    rep = family_report("config1 sod2d 256x256, 100 cycles", state, taus, sims, refs)
+    assert_parity(rep, exact_pow)
     assert (module.n_restarts(), module.n_warnings()) == sims[0].counters()
 
 
 @pytest.mark.parametrize("scheme", ["ssprk 22", "ssprk 33", "erk 11", "erk 22", "erk 43", "erk 54"])
-def test_other_schemes(oracle, oracle_vcl, scheme):
+def test_other_schemes(oracle, oracle_alt, exact_pow, scheme):
     od, module = make_product("sod2d", [64, 16])
-    sims = both(oracle, oracle_vcl, "sod2d", od.host)
+    sims = both(oracle, oracle_alt, "sod2d", od.host)
     # erk 54 takes 5 substeps per cycle with large negative stage weights and amplifies the pow()
     # noise of a shock flow faster (libm vs VCL: 3.7e-7 after 20 cycles): fewer cycles there
     cycles = 8 if scheme == "erk 54" else 20
     state, taus, refs = run_cycles(module, sims, cycles, scheme)
     rep = family_report("sod2d 64x16 %s, %d cycles" % (scheme, cycles), state, taus, sims, refs)
-    assert_within_reference_family(rep)
-    # the first cycles are still at round-off level (erk 54: ten substeps with stage weights up to
-    # 3.9 amplify a single differing pow() to 6e-10 within two cycles -- libm vs VCL on the CPU --
-    # so there the family criterion applies from the start)
-    if scheme == "erk 54":
-        state, taus, refs = run_cycles(module, sims, 2, scheme)
-        assert_within_reference_family(family_report("sod2d 64x16 erk 54, 2 cycles", state, taus, sims, refs))
+    assert_parity(rep, exact_pow)
+    state, taus, refs = run_cycles(module, sims, 2, scheme)
+    rep = family_report("sod2d 64x16 %s, 2 cycles" % scheme, state, taus, sims, refs)
+    if exact_pow or scheme != "erk 54":
+        assert rep["gpu_ref"] < 1e-13 and rep["tau_gpu_ref"] < 1e-14
     else:
-        state, taus, refs = run_cycles(module, sims[:1], 2, scheme)
-        assert rel_linf(state.download(), sims[0].get_U(0)) < 1e-13
-        assert np.max(np.abs(taus - refs[0]) / refs[0]) < 1e-14
+        assert_parity(rep, exact_pow)
 
 
 def test_vortex_3d_cycles(oracle):
@@ -334,7 +313,7 @@ def test_reference_verification_goldens(oracle, scheme, key, refinement):
         assert abs(err[name] - ref[name]) <= 1e-9 * ref[name], (name, err[name], ref[name])
 
 
-def test_restart_and_warning_semantics(oracle, oracle_vcl):
+def test_restart_and_warning_semantics(oracle, oracle_alt, exact_pow):
     """IDViolationStrategy (hyperbolic_module.template.h:1190-1210): an over-aggressive CFL
     makes the low-order update leave the bounds; raise_exception -> Restart + n_restarts,
     warn -> n_warnings; the bang-bang TimeIntegrator recovers at cfl_min exactly like the
@@ -365,15 +344,15 @@ def test_restart_and_warning_semantics(oracle, oracle_vcl):
 
     # bang-bang recovery through the TimeIntegrator
     od2, module2 = make_product("sod2d", [64, 8])
-    sims = both(oracle, oracle_vcl, "sod2d", od2.host)
+    sims = both(oracle, oracle_alt, "sod2d", od2.host)
     state, taus, refs = run_cycles(module2, sims, 10, "erk 33", cfl_min=0.3, cfl_max=3.0)
     rep = family_report("sod2d bang-bang", state, taus, sims, refs)
-    assert_within_reference_family(rep)
+    assert_parity(rep, exact_pow)
     assert (module2.n_restarts(), module2.n_warnings()) == sims[0].counters()
     assert module2.n_restarts() > 0
 
 
-def test_limiter_iterations_and_parameters(oracle, oracle_vcl):
+def test_limiter_iterations_and_parameters(oracle, oracle_alt, exact_pow):
     """non default module parameters travel through the ABI: 1 limiter iteration, evc factor,
     Riemann solver Newton iterations."""
     for mp, prm in (
@@ -385,25 +364,25 @@ def test_limiter_iterations_and_parameters(oracle, oracle_vcl):
          dict(limiter_relaxation_factor=2.0, limiter_newton_max_iterations=4)),
     ):
         od, module = make_product("sod2d", [32, 8], module_params=mp)
-        sims = both(oracle, oracle_vcl, "sod2d", od.host, **prm)
+        sims = both(oracle, oracle_alt, "sod2d", od.host, **prm)
         state, taus, refs = run_cycles(module, sims, 10, "erk 33")
         rep = family_report("sod2d %s" % mp, state, taus, sims, refs)
-        assert_within_reference_family(rep)
+        assert_parity(rep, exact_pow)
         state, taus, refs = run_cycles(module, sims[:1], 1, "erk 33")
         assert rel_linf(state.download(), sims[0].get_U(0)) < 1e-13, mp
 
 
-def test_gamma_parameter(oracle, oracle_vcl):
+def test_gamma_parameter(oracle, oracle_alt, exact_pow):
     od, module = make_product("sod2d", [32, 8], gamma=5.0 / 3.0)
-    sims = both(oracle, oracle_vcl, "sod2d", od.host, gamma=5.0 / 3.0)
+    sims = both(oracle, oracle_alt, "sod2d", od.host, gamma=5.0 / 3.0)
     state, taus, refs = run_cycles(module, sims, 10, "erk 33")
     rep = family_report("sod2d gamma 5/3", state, taus, sims, refs)
-    assert_within_reference_family(rep)
+    assert_parity(rep, exact_pow)
     state, taus, refs = run_cycles(module, sims[:1], 1, "erk 33")
     assert rel_linf(state.download(), sims[0].get_U(0)) < 1e-13
 
 
-def test_forward_facing_step_config3(oracle, oracle_vcl, oracle_rjpow):
+def test_forward_facing_step_config3(oracle, oracle_alt, exact_pow):
     """BASELINE config 3 topology (Mach 3 flow over a step; irregular rows) against the oracle."""
     import ryujin_b200 as rj
     from helpers import oracle_offline_from_host
@@ -413,29 +392,26 @@ def test_forward_facing_step_config3(oracle, oracle_vcl, oracle_rjpow):
     od = rj.OfflineData.from_mesh(mesh)
     module = rj.HyperbolicModule(od, rj.HyperbolicSystem(), rj.InitialValues(rj.InitialState.uniform, primitive=[1.4, 3.0, 1.0]))
     sims = []
-    for o in (oracle, oracle_vcl, oracle_rjpow):
+    for o in (oracle, oracle_alt):
         if o is not None:
             sims.append(oracle_offline_from_host(o, od.host).euler_sim(kind=orc.UNIFORM, primitive=(1.4, 3.0, 1.0)))
             sims[-1]._keepalive = sims[-1].off
     state, taus, refs = run_cycles(module, sims, 60, "erk 33")
-    assert_north_star_tolerance("config3 step, 60 cycles", module, state, taus, sims[-1], refs[-1])
-    sims, refs = sims[:-1], refs[:-1]
     rep = family_report("config3 step, 60 cycles", state, taus, sims, refs)
-    assert_within_reference_family(rep)
+    assert_parity(rep, exact_pow)
     assert (module.n_restarts(), module.n_warnings()) == sims[0].counters()
 
 
-def test_reference_pow_family(oracle, oracle_vcl):
-    """Smooth flow: GPU <-> oracle(libm pow) at round-off; GPU <-> oracle(VCL pow) of the size of
-    oracle(libm) <-> oracle(VCL), i.e. of the reference's own dependence on its pow / ISA."""
-    if oracle_vcl is None:
-        pytest.skip("oracle/_ref/liboracle_vcl.so not built (needs the reference tree)")
+def test_reference_pow_family(oracle, oracle_alt):
+    """Smooth flow: the GPU agrees with the parity target at round-off; the second CPU build (another
+    pow) shows how far two builds of the reference path are apart on the same case."""
     od, module = make_product("vortex3d", [24, 24, 8])
-    sims = both(oracle, oracle_vcl, "vortex3d", od.host)
+    sims = both(oracle, oracle_alt, "vortex3d", od.host)
     state, taus, refs = run_cycles(module, sims, 10, "erk 33", cfl_min=0.2, cfl_max=0.2, recovery="none")
     rep = family_report("vortex3d 24x24x8, 10 cycles", state, taus, sims, refs)
-    assert rep["gpu_port"] < 1e-12
-    assert rep["gpu_vcl"] < 4.0 * max(rep["port_vcl"], 1e-13)
+    assert rep["gpu_ref"] < 1e-12
+    if "ref_alt" in rep:
+        assert rep["gpu_alt"] < 4.0 * max(rep["ref_alt"], 1e-13)
 
 
 def test_conservation_and_symmetry_properties():

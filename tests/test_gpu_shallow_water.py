@@ -5,14 +5,16 @@ the reference's goldens in test_oracle_shallow_water.py).  Needs a B200: `-m gpu
 import numpy as np
 import pytest
 
-from helpers import (B_DYNAMIC, SW_CASES, make_sw_oracle, make_sw_product, rel_linf, rel_linf_per_component, sw_bathymetry)
+from helpers import (B_DYNAMIC, SW_CASES, make_sw_oracle, matching_oracle, make_sw_product, rel_linf, rel_linf_per_component, sw_bathymetry)
 
 pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
-def oracle(oracle_port):
-    return oracle_port
+def oracle():
+    """the oracle build whose pow() is the one the product was built for (Manning friction:
+    h^(4/3)); default: oracle/_ref/liboracle_vcl.so, the reference's own VCL pow"""
+    return matching_oracle()[0]
 
 
 def gpu_and_oracle(oracle, case, n_cells, bathymetry=False):
