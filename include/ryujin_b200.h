@@ -418,7 +418,9 @@ int rj_time_integrator_create(rj_time_integrator **out,
                               double cfl_max,
                               int cfl_recovery_strategy);
 void rj_time_integrator_destroy(rj_time_integrator *ti);
-/* step(state, t, t_final) -> tau; t_final < 0 means "no final time" */
+/* step(state, t, t_final) -> tau; t_final >= DBL_MAX (the reference's default,
+ * numeric_limits::max()) or NaN means "no final time"; any other value, negative ones included,
+ * is enforced (tau <= t_final - t) */
 int rj_time_integrator_step(rj_time_integrator *ti, rj_state *state, double t, double t_final, double *tau_out);
 double rj_time_integrator_efficiency(const rj_time_integrator *ti);
 

@@ -20,18 +20,23 @@
  * a GPU); the product is only ever built by nvcc with the definition below. */
 #ifndef RJ_LAUNCH_KERNEL
 #define RJ_LAUNCH_KERNEL(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define RJ_LAUNCH_KERNEL_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
-/* Which pow() the equation modules call (every pow of the path goes through path_pow):
- *   1  vcl_pow<false>: the reference's own pow (Agner Fog's VCL as vendored under simd-math/,
- *      called by ryujin::pow, source/simd.template.h:207-213) in its non-FMA form -- bit-identical
- *      to oracle/_ref/liboracle_vcl.so, which compiles the reference's VCL sources.  DEFAULT: this
- *      is what makes shock flows agree with the reference path to north_star's 1e-12.
- *   2  vcl_pow<true>: VCL as it compiles on an FMA host (AVX2 / AVX-512 builds of the reference).
- *   0  rj_pow (accurate_pow.h): 0.50x ulp table-driven pow, ~libm; faster, but not the
- *      reference's rounding (kept as a build option: make RJ_POW=accurate). */
+/* Which pow() the equation modules call (every pow of the path goes through path_pow): the
+ * reference's own pow -- Agner Fog's VCL as vendored under simd-math/, called by ryujin::pow,
+ * source/simd.template.h:207-213 -- restated lane-wise in vcl_pow.h.  VCL has two arithmetic forms:
+ *   2  vcl_pow<true>: as it compiles on an FMA host (AVX2 / AVX-512 builds of the reference, i.e.
+ *      any current x86 server including the hosts of the GPU boxes); bit-identical to
+ *      oracle/_ref/liboracle_vcl_fma.so.  DEFAULT (libryujin_b200.so): half the FP64 instructions
+ *      of the non-FMA form (one fused operation instead of a 17-operation Dekker product).
+ *   1  vcl_pow<false>: the non-FMA form (SSE2 ... AVX builds); bit-identical to
+ *      oracle/_ref/liboracle_vcl.so.  Built as libryujin_b200_vcl.so; the parity suite runs both.
+ * Either makes shock flows agree with the oracle to north_star's 1e-12 (in fact to the last bit).
+ *   0  rj_pow (accurate_pow.h): 0.50x ulp table-driven pow, ~libm; fastest, but not the
+ *      reference's rounding (build option: make RJ_POW=accurate). */
 #ifndef RJ_POW_IMPL
-#define RJ_POW_IMPL 1
+#define RJ_POW_IMPL 2
 #endif
 
 namespace rjb

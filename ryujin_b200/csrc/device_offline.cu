@@ -136,8 +136,13 @@ namespace rjb
             const uint32_t j = host_column(d, i, c);
             if (j >= d.n_relevant)
               throw InvalidArgument("rj_offline_create: column index out of range");
-            if (j >= n_owned)
+            if (j >= n_owned) {
               ghost_row_start[j - n_owned + 1]++;
+              /* the two-stream overlap launches rows [0, n_export) before the exchange: every row
+               * that reads a ghost column has to be one of them (offline_data.h:136-169) */
+              if (i >= d.n_export)
+                od->export_rows_first = false;
+            }
           }
         for (uint32_t q = 0; q < n_ghost; ++q)
           ghost_row_start[q + 1] += ghost_row_start[q];
@@ -331,6 +336,8 @@ namespace rjb
           nb.mat_send_offset = uint32_t(mat_send.size());
           for (uint32_t s = d.send_offsets[p]; s < d.send_offsets[p + 1]; ++s) {
             const uint32_t row = d.send_indices[s];
+            if (row >= d.n_export)
+              od->export_rows_first = false; /* ... and so has every row that is sent */
             if (row >= n_owned)
               throw InvalidArgument("rj_offline_create: send index out of range");
             send_rows.push_back(row);

@@ -72,6 +72,10 @@ struct rj_offline {
   std::vector<uint32_t> h_cols, h_transposed; /* host-only layouts */
   std::vector<uint32_t> h_send_rows, h_mat_send_entries;
   bool host_only = false;
+  /* all rows with ghost columns and all send rows lie in [0, n_export): precondition of the
+   * export-rows-first overlap of the module (violated by e.g. an imported stencil that does not
+   * declare its export range: the module then exchanges after the full sweep) */
+  bool export_rows_first = true;
 
   uint32_t entry(uint32_t row, uint32_t col) const
   {

@@ -54,8 +54,17 @@
 #define RJ_HO2_COND(col, len) ((col) < (len))
 #define RJ_HO2_NEXT(col) (++(col))
 #endif
-#ifndef RJ_PREFETCH_INDEX
-#define RJ_PREFETCH_INDEX 0
+#ifndef RJ_PREFETCH_ALPHA
+#define RJ_PREFETCH_ALPHA 0
+#endif
+#ifndef RJ_PREFETCH_LOW
+#define RJ_PREFETCH_LOW 1
+#endif
+#ifndef RJ_PREFETCH_PIJ
+#define RJ_PREFETCH_PIJ 1
+#endif
+#ifndef RJ_PREFETCH_HO
+#define RJ_PREFETCH_HO 0
 #endif
 #ifndef RJ_ALPHA_EDGE
 #define RJ_ALPHA_EDGE 0 /* 1: edge-parallel alpha_i with an ordered reduction (experimental, not measured yet) */
@@ -174,26 +183,26 @@ namespace rjb
       v[size_t(q) * ld + i] = in[q];
   }
 
-  /* Software pipelining of the index -> gather chain of the row-parallel sweeps (experimental,
-   * RJ_PREFETCH_INDEX=1, not measured yet): the column (or transposed) index of the NEXT column is
-   * loaded before the gathers of the current one are consumed, so that the two dependent memory
-   * latencies of an iteration overlap.  Same loads, same arithmetic, different issue order.  With
-   * the default 0 the macros expand to the plain indexed load. */
-#if RJ_PREFETCH_INDEX
+  /* Software pipelining of the index -> gather chain of the row-parallel sweeps: the column (or
+   * transposed) index of the NEXT column is loaded before the gathers of the current one are
+   * consumed, so that the two dependent memory latencies of an iteration overlap.  Same loads, same
+   * arithmetic, different issue order.  Per kernel (measured on 8.0M DoFs, profiles/r2a_variants.txt:
+   * k_low_order 8.32 -> 8.08 ms, k_pij_lij 5.35 -> 4.75 ms, k_alpha 2.47 -> 2.69 ms, k_high_order
+   * unchanged): on for step 4 and step 5 only. */
+  template <bool prefetch>
   RJ_DEVICE uint32_t
   pipelined_index(const uint32_t *__restrict__ idx, uint32_t e, uint32_t col, uint32_t len, uint32_t &next)
   {
-    const uint32_t current = next;
-    if (col + 1 < len)
-      next = idx[e + 32];
-    return current;
+    if (prefetch) {
+      const uint32_t current = next;
+      if (col + 1 < len)
+        next = idx[e + 32];
+      return current;
+    }
+    return idx[e];
   }
-#define RJ_INDEX_INIT(name, idx, e0) uint32_t name = (idx)[e0];
-#define RJ_INDEX(name, idx, e, col, len) pipelined_index((idx), (e), (col), (len), name)
-#else
-#define RJ_INDEX_INIT(name, idx, e0)
-#define RJ_INDEX(name, idx, e, col, len) (idx)[e]
-#endif
+#define RJ_INDEX_INIT(pf, name, idx, e0) uint32_t name = (pf) ? (idx)[e0] : 0u;
+#define RJ_INDEX(pf, name, idx, e, col, len) pipelined_index<(pf) != 0>((idx), (e), (col), (len), name)
 
   /* common row prologue: returns false if the thread has no row to work on */
   struct RowInfo {
@@ -417,11 +426,11 @@ namespace rjb
     typename Eq::Indicator indicator;
     indicator.reset(prm, prec_i, U_i);
 
-    RJ_INDEX_INIT(j_next, v.cols, r.base)
+    RJ_INDEX_INIT(RJ_PREFETCH_ALPHA, j_next, v.cols, r.base)
     RJ_UNROLL(RJ_UNROLL_ALPHA)
     for (uint32_t col = 0; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
-      const uint32_t j = RJ_INDEX(j_next, v.cols, e, col, r.len);
+      const uint32_t j = RJ_INDEX(RJ_PREFETCH_ALPHA, j_next, v.cols, e, col, r.len);
       double U_j[k], prec_j[np], aux_j[na], c_ij[dim];
       load_state<k>(U, v.ld, j, U_j);
       load_state<np>(prec, v.ld, j, prec_j);
@@ -784,11 +793,11 @@ namespace rjb
       }
     }
 
-    RJ_INDEX_INIT(j_next, v.cols, r.base)
+    RJ_INDEX_INIT(RJ_PREFETCH_LOW, j_next, v.cols, r.base)
     RJ_UNROLL(RJ_UNROLL_LOW)
     for (uint32_t col = 0; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
-      const uint32_t j = RJ_INDEX(j_next, v.cols, e, col, r.len);
+      const uint32_t j = RJ_INDEX(RJ_PREFETCH_LOW, j_next, v.cols, e, col, r.len);
 
       double U_j[k], prec_j[np], c_ij[dim];
       load_state<k>(U, v.ld, j, U_j);
@@ -962,11 +971,11 @@ namespace rjb
     const double factor = tau * m_i_inv * lambda_inv;
 
     bool all_ok = true;
-    RJ_INDEX_INIT(j_next, v.cols, r.base + 32) /* r.len > 1 */
+    RJ_INDEX_INIT(RJ_PREFETCH_PIJ, j_next, v.cols, r.base + 32) /* r.len > 1 */
     RJ_UNROLL(RJ_UNROLL_PIJ)
     for (uint32_t col = 1; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
-      const uint32_t j = RJ_INDEX(j_next, v.cols, e, col, r.len);
+      const uint32_t j = RJ_INDEX(RJ_PREFETCH_PIJ, j_next, v.cols, e, col, r.len);
       double P_ij[k], F_jH[k];
 #pragma unroll
       for (int q = 0; q < k; ++q)
@@ -1090,11 +1099,11 @@ namespace rjb
     load_state<k>(U_new, v.ld, i, U_i_new);
     const double lambda = 1. / double(r.len - 1);
 
-    RJ_INDEX_INIT(eT_next, v.transposed, r.base + 32) /* r.len > 1 */
+    RJ_INDEX_INIT(RJ_PREFETCH_HO, eT_next, v.transposed, r.base + 32) /* r.len > 1 */
     RJ_UNROLL(RJ_UNROLL_HO1)
     for (uint32_t col = 1; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
-      const double l_ij = fmin(lij[e], lij[RJ_INDEX(eT_next, v.transposed, e, col, r.len)]);
+      const double l_ij = fmin(lij[e], lij[RJ_INDEX(RJ_PREFETCH_HO, eT_next, v.transposed, e, col, r.len)]);
       const double ll = l_ij * lambda;
 #pragma unroll
       for (int q = 0; q < k; ++q)

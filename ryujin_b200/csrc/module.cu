@@ -10,10 +10,12 @@
 #include "host_offline.h"
 #include "initial_values.cuh"
 #include "kernels.cuh"
+#include "kernels_tile.cuh"
 #include "shallow_water.cuh"
 
 #include <nccl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -101,7 +103,10 @@ struct rj_hyperbolic_module {
   uint64_t launches = 0;
 
   int k = 0, n_prec = 0, n_bounds = 0, n_aux = 0;
-  uint32_t max_row_length = 0; /* longest stencil row (sizes the shared memory stage of k_alpha_edge) */
+  uint32_t max_row_length = 0; /* longest stencil row (sizes the shared memory tiles of the slice-tiled kernels) */
+  /* which sweeps run as slice-tiled kernels with bulk-copied tiles (kernels_tile.cuh); bit 0: step 5,
+   * bit 1: step 6.  RYUJIN_B200_TILE overrides the default (A/B measurements, bit-identical results) */
+  int tile_mask = RJ_TILE_DEFAULT_MASK;
 
   /* scratch, hyperbolic_module.h:319-333 */
   double *alpha = nullptr, *bounds = nullptr, *r = nullptr;
@@ -239,6 +244,38 @@ struct rj_hyperbolic_module {
     ++launches;
   }
 
+  /* slice-tiled kernels (kernels_tile.cuh): one block of `block` threads per slice and `smem`
+   * bytes of dynamic shared memory; above 48 kB the kernel needs the opt-in attribute (once) */
+  template <typename Kernel, typename... Args>
+  void launch_tile(Kernel kernel, uint32_t n_blocks, int block, size_t smem, Args... args)
+  {
+    if (n_blocks == 0)
+      return;
+    if (smem > 48 * 1024) {
+      const void *key = reinterpret_cast<const void *>(kernel);
+      if (std::find(smem_opt_in.begin(), smem_opt_in.end(), key) == smem_opt_in.end()) {
+        RJ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        smem_opt_in.push_back(key);
+      }
+    }
+    if (profiling) {
+      if (prof_used + 2 > prof_events.size()) {
+        prof_events.resize(prof_used + 2);
+        RJ_CUDA(cudaEventCreate(&prof_events[prof_used]));
+        RJ_CUDA(cudaEventCreate(&prof_events[prof_used + 1]));
+      }
+      RJ_CUDA(cudaEventRecord(prof_events[prof_used], cur));
+      RJ_LAUNCH_KERNEL_SMEM(kernel, n_blocks, block, smem, cur, args...);
+      RJ_CUDA(cudaEventRecord(prof_events[prof_used + 1], cur));
+      prof_slots.push_back(prof_slot);
+      prof_used += 2;
+    } else
+      RJ_LAUNCH_KERNEL_SMEM(kernel, n_blocks, block, smem, cur, args...);
+    RJ_CUDA(cudaGetLastError());
+    ++launches;
+  }
+  std::vector<const void *> smem_opt_in;
+
   /* profiling: slots name the kernels of one update */
   enum ProfSlot {
     P_BC = 0,
@@ -265,7 +302,10 @@ struct rj_hyperbolic_module {
   void tag(int slot) { prof_slot = slot; }
 
   /* -------- two-stream overlap -------- */
-  bool overlapping() const { return overlap && comm && comm->n_ranks > 1 && !od->neighbors.empty() && comm_stream; }
+  bool overlapping() const
+  {
+    return overlap && od->export_rows_first && comm && comm->n_ranks > 1 && !od->neighbors.empty() && comm_stream;
+  }
   /* rows [0, n_export_rows()) have ghost columns and are ghosts elsewhere; slice aligned */
   uint32_t n_export_rows() const { return std::min<uint32_t>(od->n_owned, (od->n_export + 31u) & ~31u); }
   /* what follows on the communication stream starts after everything enqueued on the main stream */
@@ -662,14 +702,24 @@ namespace rjb
       launch(k_reset_scalars, 1, 1, scalars);
 
       /* Step 2: d_ij (j > i), alpha_i; then C3 */
-      tag(P_DIJ);
-      {
+      const bool step2_tiled = (tile_mask & 4) != 0;
+      if (!step2_tiled) {
+        tag(P_DIJ);
         constexpr int W = RJ_DIJ_W; /* warps per slice in the edge-parallel d_ij kernel */
         launch(k_dij<Eq, W>, size_t(od->n_slices) * 32 * W, 32 * W, v, prm, 0u, od->n_slices, old_state.U, old_state.prec, dij);
       }
       sweep(
           [&](uint32_t b, uint32_t e) {
             tag(P_ALPHA);
+            if (step2_tiled) {
+              /* one pass: d_ij and alpha_i of the slices [b / 32, e / 32) */
+              tag(P_DIJ);
+              constexpr int W = RJ_TILE_W;
+              const uint32_t s0 = b / 32, s1 = (e + 31) / 32; /* b is slice aligned */
+              if (s1 > s0)
+                launch_tile(k_step2_tile<Eq, W>, s1 - s0, 32 * W, step2_tile_smem<Eq>(max_row_length), v, prm, s0, s1,
+                            max_row_length, old_state.U, old_state.prec, old_state.aux, dij, alpha);
+            } else
 #if RJ_ALPHA_EDGE
             if (max_row_length <= RJ_ALPHA_EDGE_MAXCOL) {
               constexpr int W = RJ_ALPHA_EDGE_W;
@@ -736,6 +786,14 @@ namespace rjb
         sweep(
             [&](uint32_t b, uint32_t e) {
               tag(P_PIJ_LIJ);
+              if (tile_mask & 1) {
+                constexpr int W = RJ_TILE_W;
+                const uint32_t s0 = b / 32, s1 = (e + 31) / 32; /* b is slice aligned */
+                if (s1 > s0)
+                  launch_tile(k_pij_lij_tile<Eq, W>, s1 - s0, 32 * W, pij_tile_smem<Eq>(max_row_length), v, prm, s0, s1,
+                              max_row_length, new_state.U, r, bounds, scalars, pij, lij);
+                return;
+              }
 #if RJ_PIJ_EDGE
               {
                 constexpr int W = RJ_PIJ_EDGE_W;
@@ -762,6 +820,14 @@ namespace rjb
           sweep(
               [&](uint32_t b, uint32_t e) {
                 tag(P_HIGH_ORDER_NEXT);
+                if (tile_mask & 2) {
+                  constexpr int W = RJ_TILE_W;
+                  const uint32_t s0 = b / 32, s1 = (e + 31) / 32;
+                  if (s1 > s0)
+                    launch_tile(k_high_order_tile<Eq, W>, s1 - s0, 32 * W, high_order_tile_smem<Eq>(max_row_length), v, prm,
+                                s0, s1, max_row_length, bounds, pij, lij, lij_next, new_state.U);
+                  return;
+                }
 #if RJ_HO_EDGE
                 if (max_row_length <= RJ_ALPHA_EDGE_MAXCOL) {
                   constexpr int W = RJ_HO_EDGE_W;
@@ -947,7 +1013,11 @@ namespace rjb
     for (const Op &op : ti.scheme.program) {
       switch (op.kind) {
       case Op::PREPARE: hm.prepare_state_vector(ti.slot(sv, op.a), op.c == 0. ? t : t + op.c * tau); break;
-      case Op::SADD: rj_state_sadd(&ti.slot(sv, op.a), op.c, op.d, &ti.slot(sv, op.b)); break;
+      case Op::SADD: {
+        const int rc = rj_state_sadd(&ti.slot(sv, op.a), op.c, op.d, &ti.slot(sv, op.b));
+        if (rc != RJ_OK)
+          return rc;
+      } break;
       case Op::STEP: {
         std::vector<const rj_state *> st;
         for (int q : op.stages)
@@ -969,7 +1039,9 @@ namespace rjb
       } break;
       }
     }
-    rj_state_swap(&sv, &ti.slot(sv, ti.scheme.result_slot));
+    const int rc_swap = rj_state_swap(&sv, &ti.slot(sv, ti.scheme.result_slot));
+    if (rc_swap != RJ_OK)
+      return rc_swap;
     tau_out = ti.scheme.tau_multiplier * tau;
     return RJ_OK;
   }
@@ -984,7 +1056,10 @@ namespace rjb
     for (const Op &op : ti.scheme.program) {
       switch (op.kind) {
       case Op::PREPARE: hm.prepare_state_vector(ti.slot(sv, op.a), 0., ti.d_cycle, op.c); break;
-      case Op::SADD: rj_state_sadd(&ti.slot(sv, op.a), op.c, op.d, &ti.slot(sv, op.b)); break;
+      case Op::SADD:
+        if (rj_state_sadd(&ti.slot(sv, op.a), op.c, op.d, &ti.slot(sv, op.b)) != RJ_OK)
+          throw CudaError(std::string("TimeIntegrator: sadd failed: ") + g_last_error);
+        break;
       case Op::STEP: {
         std::vector<const rj_state *> st;
         for (int q : op.stages)
@@ -1015,9 +1090,18 @@ namespace rjb
     else {
       /* a graph is valid for one permutation of the state pointers, one cfl and one device */
       std::vector<const void *> key;
-      key.push_back(sv.U);
-      for (auto *s : ti.temp)
+      /* every pointer and switch that is baked into the captured kernel arguments */
+      for (const rj_state *s : {static_cast<const rj_state *>(&sv)}) {
         key.push_back(s->U);
+        key.push_back(s->prec);
+        key.push_back(s->aux);
+      }
+      for (auto *s : ti.temp) {
+        key.push_back(s->U);
+        key.push_back(s->prec);
+        key.push_back(s->aux);
+      }
+      key.push_back(reinterpret_cast<const void *>(uintptr_t((hm.overlapping() ? 1u : 0u) | (unsigned(hm.tile_mask) << 1))));
       uint64_t cfl_bits;
       std::memcpy(&cfl_bits, &hm.cfl, sizeof(cfl_bits));
       key.push_back(reinterpret_cast<const void *>(cfl_bits));
@@ -1437,6 +1521,11 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
     hm->device = od->device;
     for (uint32_t len : od->h_row_length)
       hm->max_row_length = std::max(hm->max_row_length, len);
+    if (const char *e = std::getenv("RYUJIN_B200_TILE"))
+      hm->tile_mask = std::atoi(e);
+    /* the tiles of the widest slice must fit the 227 kB of shared memory of one block */
+    if (high_order_tile_smem<Euler<3>>(hm->max_row_length) > 200 * 1024)
+      hm->tile_mask = 0;
     hm->comm = comm;
     hm->eq = *eq;
     hm->mp = *mp;
@@ -1527,7 +1616,16 @@ int rj_hyperbolic_module_step(rj_hyperbolic_module *hm,
 {
   return guarded([&] {
     if (!hm || !old_state || !new_state || !tau_out)
-      throw InvalidArgument("null argument");
+      throw InvalidArgument("rj_hyperbolic_module_step: null argument");
+    if (stages < 0 || stages > 4)
+      throw InvalidArgument("rj_hyperbolic_module_step: stages must be in [0, 4]");
+    if (old_state->hm != hm || new_state->hm != hm)
+      throw InvalidArgument("rj_hyperbolic_module_step: state vector of another module");
+    if (stages > 0 && (!stage_states || !stage_weights))
+      throw InvalidArgument("rj_hyperbolic_module_step: null stage arrays with stages > 0");
+    for (int q = 0; q < stages; ++q)
+      if (!stage_states[q] || stage_states[q]->hm != hm)
+        throw InvalidArgument("rj_hyperbolic_module_step: null stage state or stage state of another module");
     return hm->step(*old_state, stages, stage_states, stage_weights, *new_state, tau, tau_max, tau_out);
   });
 }
@@ -1859,7 +1957,9 @@ int rj_time_integrator_step(rj_time_integrator *ti, rj_state *state, double t, d
     if (!ti || !state || !tau_out)
       throw InvalidArgument("null argument");
     auto &hm = *ti->hm;
-    const double tau_max = t_final < 0. ? DBL_MAX : t_final - t;
+    /* unbounded: t_final = DBL_MAX or larger (the reference's default argument is
+     * numeric_limits::max(), time_integrator.h) or NaN; a negative final time is a final time */
+    const double tau_max = (t_final != t_final || t_final >= DBL_MAX) ? DBL_MAX : t_final - t;
 
     if (ti->recovery == RJ_CFL_RECOVERY_BANG_BANG) {
       hm.strategy = RJ_STRATEGY_RAISE_EXCEPTION;

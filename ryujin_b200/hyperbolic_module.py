@@ -344,7 +344,7 @@ class TimeIntegrator:
 
     def step(self, state, t, t_final=None):
         tau = C.c_double()
-        check(lib.rj_time_integrator_step(self._h, state._h, float(t), -1.0 if t_final is None else float(t_final),
+        check(lib.rj_time_integrator_step(self._h, state._h, float(t), float("inf") if t_final is None else float(t_final),
                                           C.byref(tau)))
         return tau.value
 

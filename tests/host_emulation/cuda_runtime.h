@@ -171,7 +171,10 @@ struct rj_emu_thunk {
   virtual void run() = 0;
   virtual ~rj_emu_thunk() = default;
 };
-void rj_emu_run_grid(unsigned int grid, unsigned int block, rj_emu_thunk &kernel_call);
+void rj_emu_run_grid(unsigned int grid, unsigned int block, rj_emu_thunk &kernel_call, size_t dynamic_smem = 0);
+unsigned char *rj_emu_dynamic_smem(); /* the running block's dynamic shared memory (poisoned per block) */
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 
 template <typename F> struct rj_emu_call : rj_emu_thunk {
   F f;
@@ -179,13 +182,15 @@ template <typename F> struct rj_emu_call : rj_emu_thunk {
   void run() override { f(); }
 };
 
-/* the one launch site of the product (module.cu: launch()) goes through this macro */
-#define RJ_LAUNCH_KERNEL(kernel, grid, block, stream, ...)                                                   \
+/* the launch sites of the product (module.cu: launch(), launch_tile()) go through these macros */
+#define RJ_LAUNCH_KERNEL_SMEM(kernel, grid, block, smem, stream, ...)                                        \
   do {                                                                                                       \
     const unsigned int rj_emu_grid = (grid), rj_emu_block = (block);                                         \
+    const size_t rj_emu_smem = (smem);                                                                       \
     rj_emu_enqueue([=]() {                                                                                   \
       auto rj_emu_body = [&]() { kernel(__VA_ARGS__); };                                                     \
       rj_emu_call<decltype(rj_emu_body)> rj_emu_thunk_(rj_emu_body);                                         \
-      rj_emu_run_grid(rj_emu_grid, rj_emu_block, rj_emu_thunk_);                                             \
+      rj_emu_run_grid(rj_emu_grid, rj_emu_block, rj_emu_thunk_, rj_emu_smem);                                \
     });                                                                                                      \
   } while (0)
+#define RJ_LAUNCH_KERNEL(kernel, grid, block, stream, ...) RJ_LAUNCH_KERNEL_SMEM(kernel, grid, block, 0, stream, __VA_ARGS__)

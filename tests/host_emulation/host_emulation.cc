@@ -2,6 +2,7 @@
 // Threads of a block are ucontext coroutines, scheduled round-robin on one OS thread.
 #include "cuda_runtime.h"
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 
@@ -31,6 +32,7 @@ namespace
   thread_local unsigned int current = 0, block_threads = 0, block_done = 0, block_arrived = 0;
   thread_local unsigned long block_generation = 0;
   thread_local bool reverse_threads = false;
+  thread_local std::vector<unsigned char> dynamic_smem; /* of the running block */
 
   void yield() { swapcontext(&threads[current].context, &scheduler_context); }
 
@@ -43,6 +45,8 @@ namespace
 
   void run_block()
   {
+    /* uninitialised shared memory is poisoned like fresh device memory */
+    std::fill(dynamic_smem.begin(), dynamic_smem.end(), (unsigned char)0xff);
     if (threads.size() < block_threads)
       threads.resize(block_threads);
     block_done = block_arrived = 0;
@@ -114,8 +118,24 @@ unsigned long long rj_emu_shfl_xor(unsigned long long value, int lane_mask)
   return source < w.lanes ? w.buffer[parity][source] : value;
 }
 
-void rj_emu_run_grid(unsigned int grid, unsigned int block, rj_emu_thunk &call)
+unsigned char *rj_emu_dynamic_smem()
 {
+  /* 128-byte aligned like the device's dynamic shared memory window */
+  unsigned char *p = dynamic_smem.data();
+  return p + (128 - reinterpret_cast<uintptr_t>(p) % 128) % 128;
+}
+
+namespace rjb
+{
+  namespace tile
+  {
+    void emu_yield() { yield(); }
+  } // namespace tile
+} // namespace rjb
+
+void rj_emu_run_grid(unsigned int grid, unsigned int block, rj_emu_thunk &call, size_t smem_bytes)
+{
+  dynamic_smem.assign(smem_bytes + 128, (unsigned char)0xff);
   if (block == 0 || block > 1024)
     throw std::runtime_error("host emulation: invalid block size");
   kernel_call = &call;

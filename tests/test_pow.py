@@ -82,7 +82,10 @@ def test_default_build_uses_the_reference_pow():
     import os
 
     if not os.environ.get("RYUJIN_B200_LIB"):
-        assert rj.lib.rj_pow_implementation() == VCL
+        assert rj.lib.rj_pow_implementation() == VCL_FMA
+        second = os.path.join(os.path.dirname(rj.LIB_PATH), "libryujin_b200_vcl.so")
+        assert os.path.exists(second), "the non-FMA build of the library is missing (make -C ryujin_b200/csrc)"
+        assert ctypes.CDLL(second).rj_pow_implementation() == VCL
 
 
 def ulp_error(value, x, y):
@@ -121,6 +124,11 @@ def test_accurate_pow_against_mpmath_and_libm():
 @pytest.mark.parametrize("impl", [VCL, VCL_FMA, ACCURATE])
 def test_device_path_equals_host_path_bit_for_bit(impl):
     x, y = samples(1_000_000, 3 + impl)
+    if impl == ACCURATE:
+        # outside its fast path (|y log x| > 700, non-normal x) accurate_pow.h defers to the platform
+        # pow, which is glibc on the host and CUDA's libdevice on the device
+        keep = np.abs(y * np.log(x)) < 600.0
+        x, y = np.ascontiguousarray(x[keep]), np.ascontiguousarray(y[keep])
     host, dev = evaluate(impl, False, x, y), evaluate(impl, True, x, y)
     ok = same_bits(host, dev)
     assert ok.all(), (x[~ok][:5], y[~ok][:5], host[~ok][:5], dev[~ok][:5])

@@ -28,9 +28,9 @@ edge_all_prefetch:-DRJ_ALPHA_EDGE=1 -DRJ_PIJ_EDGE=1 -DRJ_HO_EDGE=1 -DRJ_PREFETCH
 echo "$VARIANTS" | while IFS= read -r line; do
   [ -z "$line" ] && continue
   name=${line%%:*}; flags=${line#*:}
-  rm -f build/module.o
+  rm -f build/vcl_fma/module.o
   make -s EXTRA_NVFLAGS="$flags" OUT="$OUT/lib_$name.so" 2>&1 | grep -E "error" && exit 1
   echo "built $name ($flags)"
 done
-rm -f build/module.o
+rm -f build/vcl_fma/module.o
 make -s   # restore the default object and library

@@ -1,11 +1,16 @@
 #!/bin/bash
 # On the GPU box: bench every flavour in gpurun_variants/ (5 steps, no CPU baseline) and print the
 # per-kernel times next to each other.  Results: gpurun_out/var_<name>.json
+# A name ending in _tileN runs with RYUJIN_B200_TILE=N (which sweeps run as slice-tiled kernels);
+# several _tileN names may share one library: "lib_<stem>.so" is looked up without the suffix.
 set -u
 mkdir -p gpurun_out
-for f in gpurun_variants/lib_*.so; do
-  v=$(basename "$f" .so); v=${v#lib_}
-  RYUJIN_B200_LIB=$PWD/$f python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/var_$v.json 2> gpurun_out/var_$v.err
+for v in ${VARIANT_NAMES:-$(ls gpurun_variants/lib_*.so | sed 's#.*/lib_##; s#\.so$##')}; do
+  stem=${v%_tile[0-9]*}
+  f=gpurun_variants/lib_$stem.so
+  tile=""
+  case "$v" in *_tile[0-9]*) tile=${v##*_tile};; esac
+  RYUJIN_B200_TILE=$tile RYUJIN_B200_LIB=$PWD/$f python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/var_$v.json 2> gpurun_out/var_$v.err
   python - "$v" <<'PY'
 import json, sys
 v = sys.argv[1]

@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 flt = sys.argv[1] if len(sys.argv) > 1 else "Euler<(int)3>"
-log = sys.argv[2] if len(sys.argv) > 2 else "ryujin_b200/csrc/build/module.ptxas.log"
+log = sys.argv[2] if len(sys.argv) > 2 else "ryujin_b200/csrc/build/vcl_fma/module.ptxas.log"
 s = open(log).read()
 items = re.findall(
     r"Compiling entry function '(\S+)' for 'sm_100a'\n.*?Function properties for \S+\n\s+(\d+) bytes stack frame, "
