@@ -120,13 +120,34 @@ class ClockSampler:
         }
 
 
-def workload_mesh(n_gpus, nodes=NODES):
+def block_partition(n):
+    """ranks per direction for n GPUs: 1x1x2, 1x2x2, 2x2x2 (BASELINE config 4: 2 x 2 x 2 blocks)"""
+    p = [1, 1, 1]
+    d = 2
+    while n > 1:
+        if n % 2:
+            raise SystemExit("block partition: the number of GPUs must be a power of two")
+        p[d] *= 2
+        n //= 2
+        d = (d - 1) % 3
+    return p
+
+
+def workload_mesh(n_gpus, nodes=NODES, scaling="weak", partition="slabs"):
+    """weak: `nodes`^3 DoFs PER GPU (slabs: nodes x nodes x nodes*N; blocks: nodes*p per direction);
+    strong: `nodes`^3 DoFs in total, split into slabs or blocks"""
     import ryujin_b200 as rj
 
     B = rj.Boundary
-    cells = [nodes - 1, nodes - 1, nodes * n_gpus - 1]
+    part = block_partition(n_gpus) if partition == "blocks" else [1, 1, n_gpus]
+    if scaling == "weak":
+        n_nodes = [nodes * p for p in part]
+    else:
+        n_nodes = [nodes] * 3
+    cells = [n - 1 for n in n_nodes]
     h = 10.0 / (nodes - 1)
-    return rj.CartesianMesh(cells, [-5.0, -5.0, 0.0], [h * c for c in cells], [B.dirichlet] * 6)
+    return rj.CartesianMesh(cells, [-5.0, -5.0, 0.0], [h * c for c in cells], [B.dirichlet] * 6,
+                            partition=part if n_gpus > 1 else None)
 
 
 def initial_values():
@@ -136,66 +157,131 @@ def initial_values():
                             mach_number=1.0, beta=5.0)
 
 
-def cpu_baseline(nodes, cycles, threads=None, variant="auto"):
-    """The oracle (CPU restatement of the reference path) on a bounded sample of the same
-    workload: the same vortex on a nodes^3 mesh, `cycles` ERK33 cycles after one warm-up."""
-    import ryujin_b200 as rj
-    from oracle import orc
+def host_thread_policy():
+    """Fixed thread policy of the CPU arm: the CPUs this process may actually use -- the cgroup quota
+    (the GPU boxes show 128 hardware threads but grant 16 CPUs), else the affinity mask -- capped at 64.
+    No sweep: the same box gives the same count on every run."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(round(int(quota) / int(period)))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 64))
 
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from helpers import oracle_offline_from_host
 
-    oracle = orc.Oracle(variant)
-    if threads:
-        oracle.set_threads(threads)
-    available = oracle.max_threads()
-    host = rj.HostOfflineData(workload_mesh(1, nodes))
-    off = oracle_offline_from_host(oracle, host)
-    sim = off.euler_sim(kind=orc.ISENTROPIC_VORTEX, direction=(1.0, 1.0, 0.0), position=(-1.0, -1.0, 0.0), mach=1.0, beta=5.0)
-    sim.configure_time_integrator("erk 33", CFL, CFL, "none")
-    # initial state from the oracle's own InitialValues at the generator's positions
-    from helpers import initial_state_host
+class CpuArm:
+    """The reference path on the host cores: the CPU restatement (oracle/) linked with the reference's
+    own pow (VCL, FMA form: oracle/_ref/liboracle_vcl_fma.so, built -march=x86-64-v3), FTZ/DAZ as
+    source/main.cc:26-36, OpenMP over rows.  The mesh comes from the oracle's own assembly
+    (orc_mesh.h): this arm never loads the product library.  Rows are processed one at a time
+    (scalar port, not the reference's SIMD groups of 4-8 rows) -- a reported baseline only.
 
-    sim.set_U(initial_state_host(oracle, "vortex3d", host, 0.0), 0)
-    t = sim.time_step(0.0)  # warm-up
-    # The GPU boxes expose many hardware threads that are shared with other tenants: more OpenMP
-    # threads is not always faster.  Time one cycle per candidate count and keep the fastest, so
-    # that the CPU arm is the best the host can do, not an artefact of oversubscription.
-    cores, sweep = available, {}
-    if not threads:
-        for cand in sorted({available, max(available // 2, 1), max(available // 4, 1), min(16, available), min(8, available)}):
-            oracle.set_threads(cand)
-            t0 = time.perf_counter()
-            t += sim.time_step(t)
-            sweep[cand] = time.perf_counter() - t0
-        cores = min(sweep, key=sweep.get)
-        oracle.set_threads(cores)
-    t0 = time.perf_counter()
-    for _ in range(cycles):
-        t += sim.time_step(t)
-    dt = time.perf_counter() - t0
-    value = host.n_owned * SUBSTEPS * cycles / dt / 1e6
+    Workload = the bench workload (same vortex, same boundary data, ERK33 at cfl 0.2) on a bounded
+    sample mesh of `nodes`^3 DoFs; a step is ONE forward-Euler update of it (the three updates of an
+    ERK33 cycle in rotation, so stage costs average as in MQ/s)."""
+
+    def __init__(self, nodes, timing=True):
+        from oracle import orc
+
+        self.orc = orc
+        # timing: the -O3 / -march / contraction-on build (what a production build of the reference
+        # gets); checking: the contraction-free build the product is bit-comparable with
+        variant = "native" if timing else "vcl_fma"
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "liboracle_%s.so" % variant)):
+            variant = "auto"
+        self.oracle = orc.Oracle(variant)
+        self.threads_available = self.oracle.max_threads()
+        self.threads = min(host_thread_policy(), self.threads_available) if self.threads_available > 1 else 1
+        self.oracle.set_threads(self.threads)
+        self.ftz_threads = self.oracle.flush_denormals_to_zero(timing)
+        t0 = time.perf_counter()
+        h = 10.0 / (nodes - 1)
+        self.off = self.oracle.assemble([nodes - 1] * 3, [-5.0, -5.0, 0.0], [h] * 3, [orc.DIRICHLET] * 6)
+        self.sim = self.off.euler_sim(kind=orc.ISENTROPIC_VORTEX, direction=(1.0, 1.0, 0.0), position=(-1.0, -1.0, 0.0),
+                                      mach=1.0, beta=5.0)
+        self.sim.set_cfl(CFL)
+        self.sim.interpolate(0.0, 0)
+        self.sim_initial = self.sim.get_U(0).reshape(self.off.n, -1).copy()
+        self.n_dofs = self.off.n
+        self.nodes = nodes
+        self.setup_s = time.perf_counter() - t0
+        self.t, self.tau, self.phase = 0.0, 0.0, 0
+        self.updates = 0
+
+    def update(self):
+        """one forward-Euler update: the substeps of ERK33 (time_integrator.template.h:373-403) in
+        rotation on the oracle's state slots 0..3"""
+        sim = self.sim
+        if self.phase == 0:
+            sim.prepare_state_vector(0, self.t)
+            self.tau = sim.step(0, [], [], 1)
+        elif self.phase == 1:
+            sim.prepare_state_vector(1, self.t + self.tau)
+            sim.step(1, [0], [-1.0], 2, self.tau)
+        else:
+            sim.prepare_state_vector(2, self.t + 2.0 * self.tau)
+            sim.step(2, [0, 1], [0.75, -2.0], 3, self.tau)
+            sim.set_U(sim.get_U(3), 0)
+            self.t += 3.0 * self.tau
+        self.phase = (self.phase + 1) % 3
+        self.updates += 1
+
+    def run(self, warmup, steps):
+        for _ in range(warmup):
+            self.update()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.update()
+        dt = time.perf_counter() - t0
+        value = self.n_dofs * steps / dt / 1e6
+        return {
+            "value": value,
+            "unit": "MDoF-updates/s",
+            "cores": self.threads,
+            "kind": "port",
+            "pow": self.oracle.kind + (" (FMA form)" if "_ref" in self.oracle.path and "vcl.so" not in self.oracle.path else ""),
+            "build": "-O3 -march=x86-64-v3, FP contraction on" if "native" in self.oracle.path else "-O2, contraction off",
+            "library": os.path.relpath(self.oracle.path, ROOT),
+            "simd": "scalar rows (the reference processes SIMD groups of 4-8 rows)",
+            "ftz_daz": self.ftz_threads > 0,
+            "sample": "same workload on a %d^3 = %d DoF block of the mesh, %d forward-Euler updates (ERK33 substeps in rotation) "
+                      "after %d warm-up updates, in %.2f s" % (self.nodes, self.n_dofs, steps, warmup, dt),
+            "per_core": value / self.threads,
+            "reference_prm_comment_per_core": 0.28,
+            "threads_available": self.threads_available,
+            "thread_policy": "cgroup quota / affinity, capped at 64; no sweep",
+            "setup_seconds": self.setup_s,
+        }, dt / steps
+
+
+def workload_config(nodes, world, scaling="weak", partition="slabs"):
+    part = block_partition(world) if partition == "blocks" else [1, 1, world]
+    n_nodes = [nodes * p for p in part] if scaling == "weak" else [nodes] * 3
+    n_dofs = n_nodes[0] * n_nodes[1] * n_nodes[2]
     return {
-        "value": value,
-        "unit": "MDoF-updates/s",
-        "cores": cores,
-        "kind": "port",
-        "pow": oracle.kind,
-        "sample": "same workload on %d^3 = %d DoFs, %d ERK33 cycles (%d updates) in %.2f s" % (nodes, host.n_owned, cycles, cycles * SUBSTEPS, dt),
-        "per_core": value / cores,
-        "threads_available": available,
-        "thread_sweep_s_per_cycle": {str(c): round(v, 4) for c, v in sorted(sweep.items())},
-    }, dt / cycles
+        "workload": "BASELINE configs[%d]: 3D Euler isentropic vortex (mach 1, beta 5, gamma 1.4), uniform hex mesh "
+                    "%d x %d x %d nodes, time dependent dirichlet on all faces, ERK33 (cfl %.1f), limiter iterations 2"
+                    % (1 if world == 1 else 3, n_nodes[0], n_nodes[1], n_nodes[2], CFL),
+        "n_dofs": n_dofs,
+        "n_dofs_per_gpu": n_dofs // world,
+        "substeps_per_step": SUBSTEPS,
+        "parallelism": ("%d x %d x %d blocks (%s), NCCL ghost exchange" % (part[0], part[1], part[2], partition)) if world > 1
+                       else "single GPU",
+    }
 
 
 def run_reference(args):
     """CPU arm: the reference's path on the host cores (oracle; the reference itself needs
-    deal.II + MPI + p4est and cannot be built here)."""
+    deal.II + MPI + p4est and cannot be built here).  Same config / metric / unit as our
+    arm; each step is a bounded sample of the workload (CpuArm)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nodes = args.cpu_nodes
-    base, sec_per_cycle = cpu_baseline(nodes, max(args.steps, 1))
+    arm = CpuArm(args.cpu_nodes)
+    base, sec_per_step = arm.run(args.warmup, max(args.steps, 1))
     line = {
         "impl": "reference",
         "metric": "MDoF-updates/s",
@@ -204,18 +290,13 @@ def run_reference(args):
         "n_gpus": args.gpus,
         "steps": args.steps,
         "warmup": args.warmup,
-        "ms_per_step": sec_per_cycle * 1e3,
+        "ms_per_step": sec_per_step * 1e3,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {
-            "workload": "3D Euler isentropic vortex (mach 1, beta 5), uniform hex mesh, dirichlet on all faces, ERK33; "
-                        "CPU arm runs a bounded sample of it",
-            "sample_n_dofs": nodes**3,
-            "substeps_per_step": SUBSTEPS,
-        },
+        "config": workload_config(args.nodes, args.gpus, args.scaling, args.partition),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "MDoF-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -242,7 +323,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         comm = rj.Communicator.from_torch_distributed(local_rank)
 
-    mesh = workload_mesh(world, args.nodes)
+    mesh = workload_mesh(world, args.nodes, args.scaling, args.partition)
     t_setup = time.perf_counter()
     od = rj.OfflineData.from_mesh(mesh, rank=rank, n_ranks=world, device=local_rank)
     module = rj.HyperbolicModule(od, rj.HyperbolicSystem(), initial_values(), rj.ModuleParameters(), comm=comm)
@@ -335,8 +416,11 @@ def run_ours(args):
     dom_ms, dom_count = kernel_ms[dominant]
     # low_order reads one extra state vector per ERK stage: (0 + 1 + 2)/3 = 1 on average
     extra = 8 * k * 1.0 if dominant == "low_order" else 0.0
-    bytes_per_launch = (per_pass[dominant] + extra) * n_local
-    achieved = bytes_per_launch / (dom_ms / dom_count * 1e-3) / 1e9
+    # per UPDATE, not per launch: with N > 1 every exchanged sweep runs as two launches (export rows,
+    # then the interior rows), so bytes of ALL owned rows go with the summed time of both launches
+    n_updates = prof_steps * SUBSTEPS
+    bytes_per_update = (per_pass[dominant] + extra) * n_local
+    achieved = bytes_per_update / (dom_ms / n_updates * 1e-3) / 1e9
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tfile):
@@ -353,6 +437,8 @@ def run_ours(args):
         "traffic": traffic,
         "algorithmic_bytes_per_dof": per_pass[dominant] + extra,
         "avg_launch_ms": dom_ms / dom_count,
+        "ms_per_update": dom_ms / n_updates,
+        "launches_per_update": dom_count / n_updates,
         "share_of_step": dom_ms / total_prof_ms,
         "whole_update": {
             "algorithmic_bytes_per_dof": b_alg,
@@ -362,10 +448,49 @@ def run_ours(args):
         },
         "kernel_ms_per_update": {n: v[0] / (prof_steps * SUBSTEPS) for n, v in kernel_ms.items()},
     }
+    # second roofline: the two FP64-issue bound sweeps (steps 2 and 4) against the FP64 pipe.
+    # Peak = 148 SMs x 64 FP64 lanes x clock (DFMA counted as 2 flop); the kernels execute mul and add
+    # separately (-fmad=false, bit parity with the reference), so the instruction-issue ceiling is the
+    # meaningful one: warp-instructions/s = 148 x 2 per clock.
+    fp64_file = os.path.join(ROOT, "profiles", "fp64_instructions.json")
+    if os.path.exists(fp64_file) and clocks and clocks.get("sm_mhz"):
+        with open(fp64_file) as f:
+            counts = json.load(f)
+        issue_peak = 148 * 2 * clocks["sm_mhz"] * 1e6  # FP64 warp-instructions per second
+        fp64 = {}
+        for name in ("dij", "low_order"):
+            if name in counts and name in kernel_ms:
+                per_dof = counts[name]["fp64_warp_instructions_per_dof"]
+                rate = per_dof * n_local / (kernel_ms[name][0] / n_updates * 1e-3)
+                fp64[name] = {"bound": "fp64-issue", "achieved": rate / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-inst/s",
+                              "frac": rate / issue_peak, "source": counts[name].get("source")}
+        roofline["fp64"] = fp64
 
-    base = None
+    base, parity = None, None
     if not args.no_cpu_baseline:
-        base, _ = cpu_baseline(args.cpu_nodes, args.cpu_cycles)
+        n_cpu = 3 * max(1, args.cpu_cycles)
+        base, _ = CpuArm(args.cpu_nodes).run(3, n_cpu)
+        # the result of the GPU path is CHECKED against the CPU oracle (north_star: 1e-12), not merely
+        # finite: the same ERK33 cycles from the same initial state on a block of the mesh, oracle build
+        # with contraction off (the parity target of the test suite)
+        arm = CpuArm(args.check_nodes, timing=False)
+        arm.run(0, 3 * args.check_cycles)
+        n_cycles = args.check_cycles
+        mesh_s = workload_mesh(1, args.check_nodes)
+        od_s = rj.OfflineData.from_mesh(mesh_s, device=local_rank)
+        module_s = rj.HyperbolicModule(od_s, rj.HyperbolicSystem(), initial_values(), rj.ModuleParameters())
+        ti_s = rj.TimeIntegrator(module_s, rj.TimeSteppingScheme.erk_33, CFL, CFL, rj.CFLRecoveryStrategy.none)
+        st = module_s.state_vector()
+        st.upload(arm.sim_initial)
+        t_s = 0.0
+        for _ in range(n_cycles):
+            t_s += ti_s.step(st, t_s)
+        U_gpu, U_cpu = st.download(), arm.sim.get_U(0).reshape(-1, k)
+        scale = float(np.max(np.abs(U_cpu)))
+        parity = {"mesh": "%d^3" % args.check_nodes, "erk33_cycles": n_cycles, "rel_linf_vs_oracle": float(np.max(np.abs(U_gpu - U_cpu)) / scale),
+                  "t_gpu": t_s, "t_oracle": arm.t, "oracle": os.path.relpath(arm.oracle.path, ROOT),
+                  "tolerance": 1e-12}
+        parity["ok"] = bool(parity["rel_linf_vs_oracle"] <= 1e-12)
 
     line = {
         "metric": "MDoF-updates/s",
@@ -376,21 +501,17 @@ def run_ours(args):
         "warmup": args.warmup,
         "ms_per_step": ms / args.steps,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {
-            "workload": "BASELINE configs[%d]: 3D Euler isentropic vortex (mach 1, beta 5, gamma 1.4), uniform hex mesh "
-                        "%d x %d x %d nodes, time dependent dirichlet on all faces, ERK33 (cfl %.1f), limiter iterations 2"
-                        % (1 if world == 1 else 3, args.nodes, args.nodes, args.nodes * world, CFL),
-            "n_dofs": n_global,
-            "n_dofs_per_gpu": n_local,
-            "substeps_per_step": SUBSTEPS,
-            "parallelism": "z-slabs x%d, NCCL ghost exchange" % world if world > 1 else "single GPU",
+        "config": workload_config(args.nodes, world, args.scaling, args.partition),
+        "run_info": {
             "l2": "inputs (%.1f GB of stencil + state per GPU) are far larger than the 126 MB L2; no flush needed"
                   % (od.n_entries_owned * (8 * (3 + 1 + 1 + 2 + k) + 8) / 1e9),
             "setup_seconds": t_setup,
+            "pow": {0: "accurate", 1: "vcl", 2: "vcl_fma"}[int(rj.lib.rj_pow_implementation())],
+            "tile_mask": os.environ.get("RYUJIN_B200_TILE", "default"),
         },
         "clocks": clocks,
         "e2e": {
@@ -401,6 +522,7 @@ def run_ours(args):
             "steps": e2e_steps,
             "ms_per_step": ms_e2e / e2e_steps,
             "result_finite": finite,
+            "result_check": parity,
         },
         "gpu_launches": int(launches),
         "roofline": roofline,
@@ -409,6 +531,8 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("bench.py: the GPU result deviates from the oracle: %r" % parity)
 
 
 def _quiet_stdout():
@@ -442,9 +566,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nodes", type=int, default=NODES, help="nodes per direction and GPU (default 200: 8.0M DoFs)")
-    ap.add_argument("--cpu-nodes", type=int, default=64, help="edge of the CPU sample mesh")
-    ap.add_argument("--cpu-cycles", type=int, default=3)
+    ap.add_argument("--nodes", type=int, default=NODES,
+                    help="nodes per direction: per GPU with --scaling weak (default 200: 8.0M DoFs per GPU), of the whole mesh with "
+                         "--scaling strong")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--partition", default="slabs", choices=["slabs", "blocks"],
+                    help="slabs along z (default) or blocks 1x1x2 / 1x2x2 / 2x2x2 (BASELINE config 4: 400^3 in 2x2x2 blocks)")
+    ap.add_argument("--cpu-nodes", type=int, default=128, help="edge of the CPU arm's sample block of the mesh")
+    ap.add_argument("--cpu-cycles", type=int, default=2, help="timed ERK33 cycles of the cpu_baseline leg of our arm")
+    ap.add_argument("--check-nodes", type=int, default=96, help="edge of the mesh block of the in-bench parity check")
+    ap.add_argument("--check-cycles", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

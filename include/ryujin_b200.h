@@ -225,6 +225,9 @@ typedef struct rj_mesh_desc {
   const uint8_t *cell_mask; /* NULL = all cells active; x fastest */
   int32_t box_boundary_ids[6]; /* faces x-,x+,y-,y+,z-,z+ of the bounding box */
   int32_t masked_boundary_id;  /* faces bordering an inactive cell */
+  /* ranks per direction (x fastest): rank r owns block (r % p0, (r / p0) % p1, r / (p0 p1)) of the
+   * node grid, e.g. {2, 2, 2} for BASELINE config 4.  All zero = slabs along the last axis. */
+  uint32_t partition[3];
 } rj_mesh_desc;
 
 typedef struct rj_host_offline rj_host_offline;
@@ -400,8 +403,10 @@ uint64_t rj_hyperbolic_module_kernel_launches(const rj_hyperbolic_module *hm);
  * around every launch while profiling is on (bench.py roofline).  Slots:
  * 0 boundary conditions, 1 precompute, 2 d_ij (edge parallel), 3 alpha,
  * 4 boundary d_ij, 5 d_ii + tau, 6 low-order update, 7 P_ij + l_ij,
- * 8 high-order + next l_ij, 9 final high-order update, 10 plumbing. */
-#define RJ_N_PROFILE_SLOTS 11
+ * 8 high-order + next l_ij, 9 final high-order update, 10 plumbing,
+ * 11 main stream blocked on the communication stream (exposed halo exchange),
+ * 12 scalar all-reduces. */
+#define RJ_N_PROFILE_SLOTS 13
 int rj_hyperbolic_module_set_profiling(rj_hyperbolic_module *hm, int on);
 int rj_hyperbolic_module_get_profile(rj_hyperbolic_module *hm, double ms[RJ_N_PROFILE_SLOTS], uint64_t counts[RJ_N_PROFILE_SLOTS]);
 

@@ -487,6 +487,30 @@ int orc_max_threads()
 #endif
 }
 
+/* FTZ / DAZ on every OpenMP thread, as the reference's main() does on x86-64
+ * (source/main.cc:26-36, flush_denormals_to_zero).  Only bench.py's CPU arm calls this: the
+ * parity tests keep IEEE gradual underflow, which is what the GPU's FP64 units implement. */
+int orc_flush_denormals_to_zero(int on)
+{
+#if defined(__x86_64__)
+  int n = 0;
+#pragma omp parallel reduction(+ : n)
+  {
+    unsigned int mxcsr = __builtin_ia32_stmxcsr();
+    if (on)
+      mxcsr |= (1u << 6) | (1u << 15);
+    else
+      mxcsr &= ~((1u << 6) | (1u << 15));
+    __builtin_ia32_ldmxcsr(mxcsr);
+    n += 1;
+  }
+  return n;
+#else
+  (void)on;
+  return 0;
+#endif
+}
+
 void orc_set_threads(int n)
 {
 #ifdef _OPENMP

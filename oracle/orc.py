@@ -147,6 +147,8 @@ class Oracle:
             path = vcl
         elif variant == "vcl_fma":
             path = os.path.join(_HERE, "_ref", "liboracle_vcl_fma.so")
+        elif variant == "native":  # timing build (-O3, contraction on): bench.py's CPU arm only
+            path = os.path.join(_HERE, "_ref", "liboracle_native.so")
         elif variant == "port":
             path = port
         elif variant == "fma":
@@ -183,6 +185,10 @@ class Oracle:
 
     def set_threads(self, n):
         self.lib.orc_set_threads(int(n))
+
+    def flush_denormals_to_zero(self, on=True):
+        """FTZ/DAZ on all OpenMP threads (source/main.cc:26-36); timing runs only"""
+        return int(self.lib.orc_flush_denormals_to_zero(int(bool(on))))
 
     def pow(self, x, b):
         return float(self.lib.orc_pow(x, b))

@@ -158,27 +158,46 @@ namespace orc
     OfflineData<dim> od;
     od.n_owned = mesh.n_dofs;
 
-    /* sparsity */
-    std::vector<std::set<unsigned int>> graph(mesh.n_dofs);
-    mesh.for_each_cell([&](const std::array<unsigned int, dim> &cell) {
-      unsigned int dofs[nv];
-      for (int v = 0; v < nv; ++v)
-        dofs[v] = mesh.node_to_dof[mesh.node_index(mesh.vertex(cell, v))];
-      for (int a = 0; a < nv; ++a)
-        for (int b = 0; b < nv; ++b)
-          graph[dofs[a]].insert(dofs[b]);
-    });
+    /* sparsity: row i couples to the vertices of the active cells around node i.  Rows are
+     * independent, so they are built in parallel (the 8M-DoF meshes of bench.py's CPU arm);
+     * diagonal first, then ascending -- the order the serial set-based construction produced */
+    auto adjacent_dofs = [&](unsigned int i, unsigned int *out) -> unsigned int {
+      const auto &node = mesh.dof_to_node[i];
+      unsigned int n = 0;
+      for (int o = 0; o < nv; ++o) {
+        std::array<int, dim> cell_s;
+        for (int d = 0; d < dim; ++d)
+          cell_s[d] = int(node[d]) - ((o >> d) & 1);
+        if (!mesh.cell_active(cell_s))
+          continue;
+        std::array<unsigned int, dim> cell;
+        for (int d = 0; d < dim; ++d)
+          cell[d] = cell_s[d];
+        for (int v = 0; v < nv; ++v)
+          out[n++] = mesh.node_to_dof[mesh.node_index(mesh.vertex(cell, v))];
+      }
+      std::sort(out, out + n);
+      return (unsigned int)(std::unique(out, out + n) - out);
+    };
 
     od.row_ptr.assign(mesh.n_dofs + 1, 0);
-    for (unsigned int i = 0; i < mesh.n_dofs; ++i)
-      od.row_ptr[i + 1] = od.row_ptr[i] + graph[i].size();
-    od.cols.resize(od.row_ptr.back());
+#pragma omp parallel for schedule(static)
     for (unsigned int i = 0; i < mesh.n_dofs; ++i) {
+      unsigned int buffer[nv * nv];
+      od.row_ptr[i + 1] = adjacent_dofs(i, buffer);
+    }
+    for (unsigned int i = 0; i < mesh.n_dofs; ++i)
+      od.row_ptr[i + 1] += od.row_ptr[i];
+    od.cols.resize(od.row_ptr.back());
+#pragma omp parallel for schedule(static)
+    for (unsigned int i = 0; i < mesh.n_dofs; ++i) {
+      unsigned int buffer[nv * nv];
+      const unsigned int n = adjacent_dofs(i, buffer);
       unsigned int e = od.row_ptr[i];
       od.cols[e++] = i;
-      for (unsigned int j : graph[i])
-        if (j != i)
-          od.cols[e++] = j;
+      for (unsigned int q = 0; q < n; ++q)
+        if (buffer[q] != i)
+          od.cols[e++] = buffer[q];
     }
     od.build_transposed();
 
@@ -253,22 +272,37 @@ namespace orc
     }
 
     od.measure_of_omega = 0.;
-    mesh.for_each_cell([&](const std::array<unsigned int, dim> &cell) {
-      unsigned int dofs[nv];
-      for (int v = 0; v < nv; ++v)
-        dofs[v] = mesh.node_to_dof[mesh.node_index(mesh.vertex(cell, v))];
-      od.measure_of_omega += measure_per_cell;
-      for (int a = 0; a < nv; ++a)
+    mesh.for_each_cell([&](const std::array<unsigned int, dim> &) { od.measure_of_omega += measure_per_cell; });
+    /* entry (i, j) = sum over the cells that contain both nodes, added in lexicographic cell order
+     * (what a serial loop over the cells does); row i only receives contributions from the cells
+     * around node i, so the rows are assembled independently and in parallel */
+#pragma omp parallel for schedule(static)
+    for (unsigned int i = 0; i < mesh.n_dofs; ++i) {
+      const auto &node = mesh.dof_to_node[i];
+      for (int o = nv - 1; o >= 0; --o) { /* offset bits descending = cell index ascending */
+        std::array<int, dim> cell_s;
+        int a = 0;
+        for (int d = 0; d < dim; ++d) {
+          cell_s[d] = int(node[d]) - ((o >> d) & 1);
+          a |= ((o >> d) & 1) << d; /* local vertex of node i in that cell */
+        }
+        if (!mesh.cell_active(cell_s))
+          continue;
+        std::array<unsigned int, dim> cell;
+        for (int d = 0; d < dim; ++d)
+          cell[d] = cell_s[d];
         for (int b = 0; b < nv; ++b) {
-          const std::size_t e = find(dofs[a], dofs[b]);
+          const std::size_t e = find(i, mesh.node_to_dof[mesh.node_index(mesh.vertex(cell, b))]);
           od.mij[e] += cell_mass[a][b];
           for (int d = 0; d < dim; ++d)
             od.cij[e * dim + d] += cell_c[d][a][b];
         }
-    });
+      }
+    }
 
     od.mi.assign(mesh.n_dofs, 0.);
     od.mi_inv.assign(mesh.n_dofs, 0.);
+#pragma omp parallel for schedule(static)
     for (unsigned int i = 0; i < mesh.n_dofs; ++i) {
       double s = 0.;
       for (unsigned int e = od.row_ptr[i]; e < od.row_ptr[i + 1]; ++e)

@@ -81,6 +81,8 @@ namespace orc
     void build_transposed()
     {
       transposed.assign(cols.size(), 0u);
+      bool symmetric = true;
+#pragma omp parallel for schedule(static) reduction(&& : symmetric)
       for (unsigned int i = 0; i < n_owned; ++i)
         for (unsigned int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
           const unsigned int j = cols[e];
@@ -92,8 +94,10 @@ namespace orc
               break;
             }
           if (!found)
-            throw std::runtime_error("oracle: stencil is not symmetric");
+            symmetric = false;
         }
+      if (!symmetric)
+        throw std::runtime_error("oracle: stencil is not symmetric");
     }
   };
 

@@ -101,6 +101,7 @@ class MeshDesc(C.Structure):
         ("cell_mask", u8p),
         ("box_boundary_ids", C.c_int32 * 6),
         ("masked_boundary_id", C.c_int32),
+        ("partition", C.c_uint32 * 3),
     ]
 
 

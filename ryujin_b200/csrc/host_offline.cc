@@ -250,127 +250,176 @@ namespace rjb
 
     const CellMatrices cm(dim, g.h);
     const int nv = 1 << dim;
-    const int ax = dim - 1; /* slab axis */
 
-    int64_t plane_size = 1;
-    for (int d = 0; d < ax; ++d)
-      plane_size *= g.nn[d];
-    const int64_t n_planes = g.nn[ax];
-    if (n_planes < n_ranks)
-      throw std::runtime_error("rj_mesh_generate: more ranks than node planes");
-    const int64_t p0 = n_planes * rank / n_ranks;
-    const int64_t p1 = n_planes * (rank + 1) / n_ranks;
+    /* Partition: blocks of the node grid, P[0] x P[1] x P[2] ranks (x fastest), as p4est /
+     * deal.II hand contiguous blocks of the structured mesh to the ranks
+     * (offline_data.template.h:353-360).  Default: slabs along the last axis. */
+    int64_t P[3] = {1, 1, 1};
+    if (mesh.partition[0] == 0 && mesh.partition[1] == 0 && mesh.partition[2] == 0)
+      P[dim - 1] = n_ranks;
+    else
+      for (int d = 0; d < 3; ++d)
+        P[d] = d < dim ? std::max<int64_t>(mesh.partition[d], 1) : 1;
+    if (P[0] * P[1] * P[2] != n_ranks)
+      throw std::runtime_error("rj_mesh_generate: partition does not multiply to n_ranks");
+    for (int d = 0; d < dim; ++d)
+      if (g.nn[d] < P[d])
+        throw std::runtime_error("rj_mesh_generate: more ranks than node planes");
+    const int64_t my_block[3] = {rank % P[0], (rank / P[0]) % P[1], rank / (P[0] * P[1])};
+    int64_t lo[3], hi[3], wlo[3], whi[3];
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = g.nn[d] * my_block[d] / P[d];
+      hi[d] = g.nn[d] * (my_block[d] + 1) / P[d];
+      wlo[d] = std::max<int64_t>(lo[d] - 1, 0);
+      whi[d] = std::min<int64_t>(hi[d] + 1, g.nn[d]);
+    }
+    auto block_of = [&](int d, int64_t x) -> int64_t {
+      int64_t bq = x * P[d] / g.nn[d];
+      while (bq + 1 < P[d] && x >= g.nn[d] * (bq + 1) / P[d])
+        ++bq;
+      while (bq > 0 && x < g.nn[d] * bq / P[d])
+        --bq;
+      return bq;
+    };
+    auto owned = [&](const int64_t idx[3]) {
+      for (int d = 0; d < dim; ++d)
+        if (idx[d] < lo[d] || idx[d] >= hi[d])
+          return false;
+      return true;
+    };
+    auto owner_rank = [&](const int64_t idx[3]) -> int {
+      int64_t bq[3] = {0, 0, 0};
+      for (int d = 0; d < dim; ++d)
+        bq[d] = block_of(d, idx[d]);
+      return int(bq[0] + P[0] * (bq[1] + P[1] * bq[2]));
+    };
 
     /* global dof numbering (lexicographic over active nodes) */
     std::vector<uint32_t> global_of_node; /* only for masked meshes */
     uint64_t n_global = 0;
+    int64_t n_nodes_total = 1;
+    for (int d = 0; d < dim; ++d)
+      n_nodes_total *= g.nn[d];
     if (g.mask) {
-      const int64_t total = plane_size * n_planes;
-      if (total >= int64_t(invalid))
+      if (n_nodes_total >= int64_t(invalid))
         throw std::runtime_error("rj_mesh_generate: masked mesh too large");
-      global_of_node.assign(total, invalid);
-      for (int64_t n = 0; n < total; ++n) {
+      global_of_node.assign(n_nodes_total, invalid);
+      for (int64_t n = 0; n < n_nodes_total; ++n) {
         int64_t idx[3];
         g.node_from_lex(n, idx);
         if (g.node_active(idx))
           global_of_node[n] = uint32_t(n_global++);
       }
     } else {
-      n_global = uint64_t(plane_size) * uint64_t(n_planes);
+      n_global = uint64_t(n_nodes_total);
     }
     auto global_dof = [&](int64_t lex) -> uint64_t {
       return g.mask ? uint64_t(global_of_node[lex]) : uint64_t(lex);
     };
 
-    /* local window: planes [w0, w1) = [p0-1, p1+1) clipped */
-    const int64_t w0 = std::max<int64_t>(p0 - 1, 0);
-    const int64_t w1 = std::min<int64_t>(p1 + 1, n_planes);
-    const int64_t window = (w1 - w0) * plane_size;
+    /* local window: the owned box plus one layer of nodes, clipped */
+    int64_t wn[3] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d)
+      wn[d] = whi[d] - wlo[d];
+    const int64_t window = wn[0] * wn[1] * wn[2];
     if (window >= int64_t(invalid))
       throw std::runtime_error("rj_mesh_generate: more than 2^32 rows per rank");
     std::vector<uint32_t> local_of(window, invalid);
-    auto win = [&](int64_t lex) { return lex - w0 * plane_size; };
-
-    /* pass A: classify owned nodes */
-    /* flags: bit0 owned&active, bit1 export, bit2 sends to lower, bit3 sends to upper */
-    std::vector<uint8_t> flags(window, 0);
-#pragma omp parallel for schedule(static)
-    for (int64_t lex = p0 * plane_size; lex < p1 * plane_size; ++lex) {
+    auto win_of = [&](const int64_t idx[3]) -> int64_t {
+      int64_t r = 0;
+      for (int d = dim - 1; d >= 0; --d)
+        r = r * wn[d] + (idx[d] - wlo[d]);
+      return r;
+    };
+    auto win = [&](int64_t lex) -> int64_t {
       int64_t idx[3];
       g.node_from_lex(lex, idx);
-      uint8_t f = 0;
+      return win_of(idx);
+    };
+    /* window nodes in ascending global lexicographic order */
+    auto window_lex = [&](int64_t w, int64_t idx[3]) -> int64_t {
+      idx[0] = idx[1] = idx[2] = 0;
+      for (int d = 0; d < dim; ++d) {
+        idx[d] = wlo[d] + w % wn[d];
+        w /= wn[d];
+      }
+      return g.lex_node(idx);
+    };
+
+    /* pass A: classify the window's nodes.
+     * sendmask (owned nodes): bit o = the node shares an active cell with a node of the block at
+     * relative offset o (offset_code over {-1,0,1}^dim); non-zero = export row.
+     * ghost (other nodes): shares an active cell with an owned node. */
+    std::vector<uint32_t> sendmask(window, 0);
+    std::vector<uint8_t> kind(window, 0); /* 1 owned & active, 2 ghost */
+#pragma omp parallel for schedule(static)
+    for (int64_t w = 0; w < window; ++w) {
+      int64_t idx[3];
+      window_lex(w, idx);
+      const bool mine = owned(idx);
+      bool active = false, touches_owned = false;
+      uint32_t mask_bits = 0;
       for (int code = 0; code < nv; ++code) {
         int64_t c[3];
         g.adjacent_cell(idx, code, c);
         if (!g.cell_active(c))
           continue;
-        f |= 1;
-        if (c[ax] < p0) /* cell layer p0-1: has vertices in plane p0-1 */
-          f |= 2 | 4;
-        if (c[ax] + 1 >= p1) /* cell layer p1-1: has vertices in plane p1 */
-          f |= 2 | 8;
+        active = true;
+        for (int v = 0; v < nv; ++v) {
+          int64_t vtx[3] = {0, 0, 0};
+          for (int d = 0; d < dim; ++d)
+            vtx[d] = c[d] + ((v >> d) & 1);
+          if (owned(vtx)) {
+            touches_owned = true;
+            continue;
+          }
+          if (mine) {
+            int o[3] = {0, 0, 0};
+            for (int d = 0; d < dim; ++d)
+              o[d] = int(block_of(d, vtx[d]) - my_block[d]);
+            mask_bits |= 1u << offset_code(dim, o);
+          }
+        }
       }
-      flags[win(lex)] = f;
+      if (mine && active) {
+        kind[w] = 1;
+        sendmask[w] = mask_bits;
+      } else if (!mine && active && touches_owned)
+        kind[w] = 2;
     }
 
-    /* ghost planes */
-    std::vector<int64_t> ghosts_lower, ghosts_upper;
-    if (p0 > 0)
-      for (int64_t lex = (p0 - 1) * plane_size; lex < p0 * plane_size; ++lex) {
-        int64_t idx[3];
-        g.node_from_lex(lex, idx);
-        bool adjacent = false;
-        for (int code = 0; code < nv; ++code) {
-          int64_t c[3];
-          g.adjacent_cell(idx, code, c);
-          if (c[ax] == p0 - 1 && g.cell_active(c))
-            adjacent = true;
-        }
-        if (adjacent)
-          ghosts_lower.push_back(lex);
-      }
-    if (p1 < n_planes)
-      for (int64_t lex = p1 * plane_size; lex < (p1 + 1) * plane_size; ++lex) {
-        int64_t idx[3];
-        g.node_from_lex(lex, idx);
-        bool adjacent = false;
-        for (int code = 0; code < nv; ++code) {
-          int64_t c[3];
-          g.adjacent_cell(idx, code, c);
-          if (c[ax] == p1 - 1 && g.cell_active(c))
-            adjacent = true;
-        }
-        if (adjacent)
-          ghosts_upper.push_back(lex);
-      }
-
-    /* local numbering: export rows, other owned rows, ghosts by owner rank */
+    /* local numbering: export rows, other owned rows (both in global lexicographic order), then the
+     * ghosts grouped by owner rank (ascending), each group in global lexicographic order -- the
+     * order in which the owner sends them */
     std::vector<int64_t> node_of_local;
+    std::vector<std::pair<int, int64_t>> ghosts; /* (owner rank, lex) */
     {
       uint32_t n = 0;
+      out.n_export = 0;
       for (int pass = 0; pass < 2; ++pass)
-        for (int64_t lex = p0 * plane_size; lex < p1 * plane_size; ++lex) {
-          const uint8_t f = flags[win(lex)];
-          if (!(f & 1))
+        for (int64_t w = 0; w < window; ++w) {
+          if (kind[w] != 1)
             continue;
-          const bool is_export = (f & 2) != 0;
+          const bool is_export = sendmask[w] != 0;
           if ((pass == 0) == is_export) {
-            local_of[win(lex)] = n++;
-            node_of_local.push_back(lex);
+            int64_t idx[3];
+            local_of[w] = n++;
+            node_of_local.push_back(window_lex(w, idx));
+            if (is_export)
+              out.n_export++;
           }
         }
       out.n_owned = n;
-      out.n_export = 0;
-      for (int64_t lex = p0 * plane_size; lex < p1 * plane_size; ++lex)
-        if ((flags[win(lex)] & 3) == 3)
-          out.n_export++;
-      for (int64_t lex : ghosts_lower) {
-        local_of[win(lex)] = n++;
-        node_of_local.push_back(lex);
-      }
-      for (int64_t lex : ghosts_upper) {
-        local_of[win(lex)] = n++;
-        node_of_local.push_back(lex);
+      for (int64_t w = 0; w < window; ++w)
+        if (kind[w] == 2) {
+          int64_t idx[3];
+          const int64_t lex = window_lex(w, idx);
+          ghosts.emplace_back(owner_rank(idx), lex);
+        }
+      std::sort(ghosts.begin(), ghosts.end());
+      for (const auto &gh : ghosts) {
+        local_of[win(gh.second)] = n++;
+        node_of_local.push_back(gh.second);
       }
       out.n_relevant = n;
     }
@@ -378,23 +427,30 @@ namespace rjb
     out.n_internal = 0;
     out.n_global_dofs = n_global;
 
-    /* exchange lists */
+    /* exchange lists: one neighbour per rank that owns ghosts of this rank (ascending rank); the
+     * rows sent to it are this rank's export rows that share a cell with one of its nodes */
     out.neighbor_rank.clear();
     out.ghost_count.clear();
     out.send_offsets.assign(1, 0);
     out.send_indices.clear();
-    auto add_neighbor = [&](int nb_rank, const std::vector<int64_t> &ghosts, uint8_t send_flag) {
+    for (size_t q = 0; q < ghosts.size();) {
+      const int nb_rank = ghosts[q].first;
+      size_t q1 = q;
+      while (q1 < ghosts.size() && ghosts[q1].first == nb_rank)
+        ++q1;
       out.neighbor_rank.push_back(nb_rank);
-      out.ghost_count.push_back(uint32_t(ghosts.size()));
+      out.ghost_count.push_back(uint32_t(q1 - q));
+      const int64_t nb_block[3] = {nb_rank % P[0], (nb_rank / P[0]) % P[1], nb_rank / (P[0] * P[1])};
+      int o[3] = {0, 0, 0};
+      for (int d = 0; d < dim; ++d)
+        o[d] = int(nb_block[d] - my_block[d]);
+      const uint32_t bit = 1u << offset_code(dim, o);
       for (uint32_t i = 0; i < out.n_export; ++i)
-        if (flags[win(node_of_local[i])] & send_flag)
+        if (sendmask[win(node_of_local[i])] & bit)
           out.send_indices.push_back(i);
       out.send_offsets.push_back(uint32_t(out.send_indices.size()));
-    };
-    if (p0 > 0)
-      add_neighbor(rank - 1, ghosts_lower, 4);
-    if (p1 < n_planes)
-      add_neighbor(rank + 1, ghosts_upper, 8);
+      q = q1;
+    }
 
     /* rows: count, then fill */
     const uint32_t n_owned = out.n_owned;

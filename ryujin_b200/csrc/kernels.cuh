@@ -1259,6 +1259,57 @@ namespace rjb
     buf[t] = v[size_t(c) * ld + rows[s]];
   }
 
+  /* All neighbours of one vector exchange in ONE launch (instead of one launch, n_comp sends and
+   * n_comp receives per neighbour): the send buffer holds one contiguous block per neighbour,
+   * [component][row] inside the block, the receive buffer likewise with the neighbour's ghost
+   * rows; one ncclSend / ncclRecv per neighbour moves a whole block. */
+  constexpr int max_neighbors = 26;
+  struct ExchangePlan {
+    uint32_t n_neighbors;
+    uint32_t row_offset[max_neighbors + 1]; /* prefix sums of the rows per neighbour */
+    uint32_t ghost_start[max_neighbors];    /* unpack only: first ghost row of the neighbour */
+  };
+
+  RJ_DEVICE uint32_t plan_neighbor(const ExchangePlan &plan, uint32_t row)
+  {
+    uint32_t p = 0;
+    while (p + 1 < plan.n_neighbors && row >= plan.row_offset[p + 1])
+      ++p;
+    return p;
+  }
+
+  /* t enumerates (neighbour block, component, row) in buffer order */
+  __global__ void k_pack_blocks(ExchangePlan plan, uint32_t n_comp, uint32_t ld, const uint32_t *__restrict__ rows, const double *__restrict__ v, double *__restrict__ buf)
+  {
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint32_t n_rows = plan.row_offset[plan.n_neighbors];
+    if (t >= size_t(n_rows) * n_comp)
+      return;
+    /* block p starts at row_offset[p] * n_comp */
+    uint32_t p = 0;
+    while (p + 1 < plan.n_neighbors && t >= size_t(plan.row_offset[p + 1]) * n_comp)
+      ++p;
+    const uint32_t count = plan.row_offset[p + 1] - plan.row_offset[p];
+    const size_t local = t - size_t(plan.row_offset[p]) * n_comp;
+    const uint32_t c = uint32_t(local / count), s = uint32_t(local % count);
+    buf[t] = v[size_t(c) * ld + rows[plan.row_offset[p] + s]];
+  }
+
+  __global__ void k_unpack_blocks(ExchangePlan plan, uint32_t n_comp, uint32_t ld, const double *__restrict__ buf, double *__restrict__ v)
+  {
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint32_t n_rows = plan.row_offset[plan.n_neighbors];
+    if (t >= size_t(n_rows) * n_comp)
+      return;
+    uint32_t p = 0;
+    while (p + 1 < plan.n_neighbors && t >= size_t(plan.row_offset[p + 1]) * n_comp)
+      ++p;
+    const uint32_t count = plan.row_offset[p + 1] - plan.row_offset[p];
+    const size_t local = t - size_t(plan.row_offset[p]) * n_comp;
+    const uint32_t c = uint32_t(local / count), s = uint32_t(local % count);
+    v[size_t(c) * ld + plan.ghost_start[p] + s] = buf[t];
+  }
+
   __global__ void k_pack_entries(uint32_t n, const uint32_t *__restrict__ entries, const double *__restrict__ m, double *__restrict__ buf)
   {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -22,7 +22,7 @@ unsigned char *rj_emu_dynamic_smem(); /* tests/host_emulation/host_emulation.cc 
 #endif
 
 #ifndef RJ_TILE_DEFAULT_MASK
-#define RJ_TILE_DEFAULT_MASK 0 /* bit 0: step 5 tiled, bit 1: step 6 tiled */
+#define RJ_TILE_DEFAULT_MASK 3 /* bit 0: step 5 tiled, bit 1: step 6 tiled, bit 2: fused step 2 (slower: profiles/r2b_variants_tile_kernels.txt) */
 #endif
 #ifndef RJ_TILE_W
 #define RJ_TILE_W 4 /* warps per slice */

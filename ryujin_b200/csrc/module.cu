@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -113,7 +114,7 @@ struct rj_hyperbolic_module {
   double *dij = nullptr, *lij = nullptr, *lij_next = nullptr, *pij = nullptr;
   StepScalars *scalars = nullptr;
   StepScalars *h_scalars = nullptr; /* pinned */
-  double *send_buffer = nullptr;
+  double *send_buffer = nullptr, *recv_buffer = nullptr;
   size_t send_buffer_size = 0;
   double *staging = nullptr; /* n_owned * max(k, n_prec, n_bounds) */
   /* initial_precomputed_ of the reference (hyperbolic_module.h:309): bathymetry for the
@@ -213,6 +214,7 @@ struct rj_hyperbolic_module {
         std::max<size_t>(size_t(od->n_send_rows) * std::max(k, std::max(n_prec, n_bounds)),
                          od->n_mat_send);
     alloc(send_buffer, send_buffer_size);
+    alloc(recv_buffer, size_t(od->n_relevant - od->n_owned) * std::max(k, std::max(n_prec, n_bounds)));
     alloc(staging, size_t(od->n_owned) * std::max(k, std::max(n_prec, n_bounds)));
     if (n_initial_precomputed > 0)
       alloc(initial_precomputed, size_t(n_initial_precomputed) * ld);
@@ -242,6 +244,27 @@ struct rj_hyperbolic_module {
       RJ_LAUNCH_KERNEL(kernel, grid, block, cur, args...);
     RJ_CUDA(cudaGetLastError());
     ++launches;
+  }
+
+  /* profiling: device time of whatever `f` enqueues on the current stream, booked on `slot` */
+  template <typename F>
+  void timed_region(int slot, const F &f)
+  {
+    if (!profiling) {
+      f();
+      return;
+    }
+    if (prof_used + 2 > prof_events.size()) {
+      prof_events.resize(prof_used + 2);
+      RJ_CUDA(cudaEventCreate(&prof_events[prof_used]));
+      RJ_CUDA(cudaEventCreate(&prof_events[prof_used + 1]));
+    }
+    const size_t first = prof_used;
+    prof_used += 2;
+    prof_slots.push_back(slot); /* slot n <-> events 2n, 2n + 1 (collect_profile) */
+    RJ_CUDA(cudaEventRecord(prof_events[first], cur));
+    f();
+    RJ_CUDA(cudaEventRecord(prof_events[first + 1], cur));
   }
 
   /* slice-tiled kernels (kernels_tile.cuh): one block of `block` threads per slice and `smem`
@@ -289,6 +312,8 @@ struct rj_hyperbolic_module {
     P_HIGH_ORDER_NEXT,
     P_HIGH_ORDER_FINAL,
     P_OTHER,
+    P_COMM_WAIT, /* main stream blocked on the communication stream (exposed exchange time) */
+    P_ALLREDUCE, /* scalar all-reduces (tau_max; restart flags) */
     P_N_SLOTS
   };
   bool profiling = false;
@@ -321,8 +346,21 @@ struct rj_hyperbolic_module {
   void join_comm()
   {
     RJ_CUDA(cudaEventRecord(ev_join, comm_stream));
-    RJ_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
     cur = stream;
+    if (profiling) {
+      /* time the main stream spends blocked in this join = exposed communication */
+      if (prof_used + 2 > prof_events.size()) {
+        prof_events.resize(prof_used + 2);
+        RJ_CUDA(cudaEventCreate(&prof_events[prof_used]));
+        RJ_CUDA(cudaEventCreate(&prof_events[prof_used + 1]));
+      }
+      RJ_CUDA(cudaEventRecord(prof_events[prof_used], stream));
+      RJ_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+      RJ_CUDA(cudaEventRecord(prof_events[prof_used + 1], stream));
+      prof_slots.push_back(P_COMM_WAIT);
+      prof_used += 2;
+    } else
+      RJ_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
   }
 
   /* call after a stream synchronize */
@@ -346,36 +384,35 @@ struct rj_hyperbolic_module {
     if (!comm || od->neighbors.empty())
       return;
     const size_t ld = od->ld;
-    for (const auto &nb : od->neighbors)
-      launch(k_pack_rows,
-             size_t(nb.send_count) * n_comp,
-             256,
-             nb.send_count,
-             uint32_t(n_comp),
-             uint32_t(ld),
-             od->send_rows + nb.send_offset,
-             v,
-             send_buffer + size_t(nb.send_offset) * n_comp);
+    if (od->neighbors.size() > size_t(max_neighbors))
+      throw InvalidArgument("more than 26 neighbour ranks");
+    /* one pack launch, ONE send and ONE receive per neighbour, one unpack launch */
+    ExchangePlan send_plan{}, recv_plan{};
+    send_plan.n_neighbors = recv_plan.n_neighbors = uint32_t(od->neighbors.size());
+    uint32_t n_ghost = 0;
+    for (size_t p = 0; p < od->neighbors.size(); ++p) {
+      const auto &nb = od->neighbors[p];
+      send_plan.row_offset[p] = nb.send_offset;
+      send_plan.row_offset[p + 1] = nb.send_offset + nb.send_count;
+      recv_plan.row_offset[p] = n_ghost;
+      recv_plan.ghost_start[p] = nb.ghost_start;
+      n_ghost += nb.ghost_count;
+      recv_plan.row_offset[p + 1] = n_ghost;
+    }
+    launch(k_pack_blocks, size_t(od->n_send_rows) * n_comp, 256, send_plan, uint32_t(n_comp), uint32_t(ld), od->send_rows, v,
+           send_buffer);
     RJ_NCCL(ncclGroupStart());
-    for (const auto &nb : od->neighbors) {
-      for (int c = 0; c < n_comp; ++c) {
-        if (nb.send_count)
-          RJ_NCCL(ncclSend(send_buffer + size_t(nb.send_offset) * n_comp + size_t(c) * nb.send_count,
-                           nb.send_count,
-                           ncclDouble,
-                           nb.rank,
-                           comm->comm,
-                           cur));
-        if (nb.ghost_count)
-          RJ_NCCL(ncclRecv(v + size_t(c) * ld + nb.ghost_start,
-                           nb.ghost_count,
-                           ncclDouble,
-                           nb.rank,
-                           comm->comm,
-                           cur));
-      }
+    for (size_t p = 0; p < od->neighbors.size(); ++p) {
+      const auto &nb = od->neighbors[p];
+      if (nb.send_count)
+        RJ_NCCL(ncclSend(send_buffer + size_t(nb.send_offset) * n_comp, size_t(nb.send_count) * n_comp, ncclDouble, nb.rank,
+                         comm->comm, cur));
+      if (nb.ghost_count)
+        RJ_NCCL(ncclRecv(recv_buffer + size_t(recv_plan.row_offset[p]) * n_comp, size_t(nb.ghost_count) * n_comp, ncclDouble,
+                         nb.rank, comm->comm, cur));
     }
     RJ_NCCL(ncclGroupEnd());
+    launch(k_unpack_blocks, size_t(n_ghost) * n_comp, 256, recv_plan, uint32_t(n_comp), uint32_t(ld), recv_buffer, v);
   }
 
   void exchange_matrix(double *m)
@@ -437,6 +474,7 @@ rj_hyperbolic_module::~rj_hyperbolic_module()
   f(pij);
   f(scalars);
   f(send_buffer);
+  f(recv_buffer);
   f(staging);
   f(initial_precomputed);
   f(csr_to_sliced);
@@ -760,7 +798,9 @@ namespace rjb
       if (multi) {
         if (ov)
           fork_comm();
-        RJ_NCCL(ncclAllReduce(&scalars->tau_max, &scalars->tau_max, 1, ncclDouble, ncclMin, comm->comm, cur));
+        timed_region(P_ALLREDUCE, [&] {
+          RJ_NCCL(ncclAllReduce(&scalars->tau_max, &scalars->tau_max, 1, ncclDouble, ncclMin, comm->comm, cur));
+        });
         if (ov)
           join_comm();
       }
@@ -842,9 +882,11 @@ namespace rjb
               [&] { exchange_matrix(lij_next); });
       }
 
-      /* C9 and the host side of :571-578,1190-1210 */
+      /* C9 and the host side of :571-578,1190-1210.  Inside a device-resident cycle the flags of all
+       * substeps are reduced over the ranks ONCE, at the end of the cycle (enqueue_cycle): no
+       * substep reads another rank's flag before the host evaluates them. */
       tag(P_OTHER);
-      if (multi) {
+      if (multi && !cycle) {
         if (ov)
           fork_comm();
         RJ_NCCL(ncclAllReduce(&scalars->restart_needed, &scalars->restart_needed, 1, ncclInt, ncclMax, comm->comm, cur));
@@ -1069,6 +1111,12 @@ namespace rjb
         ++substep;
       } break;
       }
+    }
+    /* one reduction of the restart / numeric-error flags of all substeps over the ranks (C9) */
+    if (hm.comm && hm.comm->n_ranks > 1) {
+      static_assert(offsetof(CycleScalars, numeric_error) == offsetof(CycleScalars, restart) + max_substeps * sizeof(int),
+                    "restart and numeric_error flags are contiguous");
+      RJ_NCCL(ncclAllReduce(ti.d_cycle->restart, ti.d_cycle->restart, 2 * max_substeps, ncclInt, ncclMax, hm.comm->comm, hm.stream));
     }
     RJ_CUDA(cudaMemcpyAsync(&ti.h_cycle[1], ti.d_cycle, sizeof(CycleScalars), cudaMemcpyDeviceToHost, hm.stream));
     return substep;

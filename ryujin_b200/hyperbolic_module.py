@@ -300,7 +300,7 @@ class HyperbolicModule:
         return int(lib.rj_hyperbolic_module_kernel_launches(self._h))
 
     PROFILE_SLOTS = ("boundary_conditions", "precompute", "dij", "alpha", "boundary_dij", "dii_tau", "low_order",
-                     "pij_lij", "high_order_next_lij", "high_order_final", "plumbing")
+                     "pij_lij", "high_order_next_lij", "high_order_final", "plumbing", "comm_wait", "allreduce")
 
     def set_profiling(self, on):
         """per-kernel CUDA-event timing on the module's stream (bench.py roofline)"""

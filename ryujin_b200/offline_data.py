@@ -33,8 +33,12 @@ class CartesianMesh:
     step).
     """
 
-    def __init__(self, n_cells, origin, extent, boundary_ids, cell_mask=None, masked_boundary_id=Boundary.slip):
+    def __init__(self, n_cells, origin, extent, boundary_ids, cell_mask=None, masked_boundary_id=Boundary.slip,
+                 partition=None):
+        """partition: ranks per direction, e.g. (2, 2, 2) -- blocks of the node grid as the reference's
+        p4est partition hands them out (offline_data.template.h:353-360); None = slabs along the last axis"""
         self.dim = len(n_cells)
+        self.partition = [0, 0, 0] if partition is None else [int(p) for p in partition] + [1] * (3 - len(partition))
         assert 1 <= self.dim <= 3
         assert len(origin) == self.dim and len(extent) == self.dim
         assert len(boundary_ids) == 2 * self.dim
@@ -50,10 +54,10 @@ class CartesianMesh:
             self.cell_mask = m
 
     @classmethod
-    def rectangular_domain(cls, bottom_left, top_right, n_cells, boundary_ids):
+    def rectangular_domain(cls, bottom_left, top_right, n_cells, boundary_ids, partition=None):
         """geometry "rectangular domain" with 2^refinement x ... subdivisions folded into n_cells"""
         extent = [b - a for a, b in zip(bottom_left, top_right)]
-        return cls(n_cells, bottom_left, extent, boundary_ids)
+        return cls(n_cells, bottom_left, extent, boundary_ids, partition=partition)
 
     @classmethod
     def forward_facing_step(cls, refinement, length=3.0, height=1.0, step_position=0.6, step_height=0.2,
@@ -78,6 +82,8 @@ class CartesianMesh:
         for f, b in enumerate(self.boundary_ids):
             d.box_boundary_ids[f] = b
         d.masked_boundary_id = self.masked_boundary_id
+        for q in range(3):
+            d.partition[q] = self.partition[q]
         if self.cell_mask is not None:
             d.cell_mask = self.cell_mask.ctypes.data_as(_lib.u8p)
         return d

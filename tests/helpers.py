@@ -87,11 +87,11 @@ CASES = {
 KIND_ORACLE = {"uniform": orc.UNIFORM, "contrast": orc.CONTRAST, "isentropic_vortex": orc.ISENTROPIC_VORTEX}
 
 
-def make_mesh(case, n_cells):
+def make_mesh(case, n_cells, partition=None):
     import ryujin_b200 as rj
 
-    c = CASES[case]
-    return rj.CartesianMesh.rectangular_domain(c["bottom_left"], c["top_right"], n_cells, c["boundary"])
+    c = CASES[case] if case in CASES else SW_CASES[case]
+    return rj.CartesianMesh.rectangular_domain(c["bottom_left"], c["top_right"], n_cells, c["boundary"], partition=partition)
 
 
 def make_product(case, n_cells, device=0, comm=None, rank=0, n_ranks=1, module_params=None, **eq):

@@ -100,7 +100,21 @@ def test_multi_rank_module_path_with_ranks_as_threads():
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "multi-rank parity ok" in out.stdout
-    assert out.stdout.count("overlap on/off bit-identical True") == 4
+    assert out.stdout.count("overlap on/off bit-identical True") == 5
+    assert out.stdout.count("vs oracle with the same partition") == 5 and "bit-identical False" not in out.stdout
+
+
+def test_block_decomposition_with_ranks_as_threads():
+    """BASELINE config 4 asks for 2 x 2 x 2 blocks: the generator's block partition (face, edge and
+    corner neighbours) with 8 ranks as host threads, every case bit-identical to the oracle run on
+    the same partition"""
+    build()
+    env = dict(os.environ, RYUJIN_B200_LIB=EMU_LIB)
+    out = subprocess.run([sys.executable, os.path.join(EMU_DIR, "multi_rank_threads.py"), "8", "blocks"], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "multi-rank parity ok" in out.stdout
+    assert out.stdout.count("vs oracle with the same partition") == 4 and "bit-identical False" not in out.stdout
 
 
 def test_results_do_not_depend_on_the_block_and_thread_order():
