@@ -66,35 +66,8 @@
 #ifndef RJ_PREFETCH_HO
 #define RJ_PREFETCH_HO 0
 #endif
-#ifndef RJ_ALPHA_EDGE
-#define RJ_ALPHA_EDGE 0 /* 1: edge-parallel alpha_i with an ordered reduction (experimental, not measured yet) */
-#endif
-#ifndef RJ_PIJ_EDGE
-#define RJ_PIJ_EDGE 0 /* 1: edge-parallel step 5 (no reduction in that sweep at all) */
-#endif
-#ifndef RJ_PIJ_EDGE_W
-#define RJ_PIJ_EDGE_W 4
-#endif
-#ifndef RJ_MB_PIJ_EDGE
-#define RJ_MB_PIJ_EDGE 5
-#endif
-#ifndef RJ_HO_EDGE
-#define RJ_HO_EDGE 0 /* 1: edge-parallel step 6 with the slice's P_ij and l_ij staged in shared memory */
-#endif
-#ifndef RJ_HO_EDGE_W
-#define RJ_HO_EDGE_W 4
-#endif
-#ifndef RJ_MB_HO_EDGE
-#define RJ_MB_HO_EDGE 5
-#endif
-#ifndef RJ_ALPHA_EDGE_W
-#define RJ_ALPHA_EDGE_W 4
-#endif
-#ifndef RJ_ALPHA_EDGE_MAXCOL
-#define RJ_ALPHA_EDGE_MAXCOL 27 /* longest row the shared memory stage is sized for (Q1 in 3D) */
-#endif
-#ifndef RJ_MB_ALPHA_EDGE
-#define RJ_MB_ALPHA_EDGE 5
+#ifndef RJ_TILE_PREFETCH_MAXCOL
+#define RJ_TILE_PREFETCH_MAXCOL 27 /* columns whose l_ji the tiled step 6 keeps in registers (Q1 in 3D) */
 #endif
 #ifndef RJ_DIJ_W
 #define RJ_DIJ_W 4 /* warps per slice of the edge-parallel d_ij kernel */
@@ -104,15 +77,6 @@
 #endif
 #ifndef RJ_MB_LOW
 #define RJ_MB_LOW 4
-#endif
-#ifndef RJ_SPLIT_LOW
-#define RJ_SPLIT_LOW 0 /* 1: run step 4 as two lighter kernels (parts 1 + 2 of k_low_order) */
-#endif
-#ifndef RJ_MB_LOW_A
-#define RJ_MB_LOW_A 6
-#endif
-#ifndef RJ_MB_LOW_B
-#define RJ_MB_LOW_B 5
 #endif
 #ifndef RJ_MB_LOW_SW
 #define RJ_MB_LOW_SW 2 /* shallow water: star states + sources need ~200 registers */
@@ -446,84 +410,6 @@ namespace rjb
   }
 
 
-  /* ---------------------------------------------------------------------- *
-   * Experimental alternative to k_alpha (RJ_ALPHA_EDGE=1): EDGE parallel like k_dij.  A block is
-   * one slice of 32 rows x W warps; warp w evaluates the per-edge contributions of columns
-   * w, w+W, ... (the gathers of up to W columns of a row are in flight at once) into shared
-   * memory; warp 0 then adds them up IN COLUMN ORDER, exactly the additions of the row-parallel
-   * kernel, so the result is bit-identical (0 + x == x; the sign of a zero cannot differ because
-   * the accumulators start at +0).
-   * ---------------------------------------------------------------------- */
-  template <class Eq, int W, int MAXCOL>
-  __global__ void __launch_bounds__(32 * W, RJ_MB_ALPHA_EDGE) k_alpha_edge(StencilView v,
-                                                                         typename Eq::Params prm,
-                                                                         uint32_t slice_begin,
-                                                                         uint32_t slice_end,
-                                                                         const double *__restrict__ U,
-                                                                         const double *__restrict__ prec,
-                                                                         const double *__restrict__ aux,
-                                                                         double *__restrict__ alpha)
-  {
-    constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec, na = Eq::n_aux;
-    __shared__ double contribution[MAXCOL * (k + 1) * 32];
-    const uint32_t g = slice_begin + blockIdx.x;
-    if (g >= slice_end)
-      return; /* the whole block */
-    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const uint32_t i = (g << 5) + lane;
-    const bool has_row = i < v.n_owned && v.row_length[i] > 1;
-    const uint32_t len = has_row ? v.row_length[i] : 0u;
-    const uint32_t base = v.slice_offsets[g] + lane;
-
-    double U_i[k], prec_i[np];
-    typename Eq::Indicator indicator;
-    if (has_row) {
-      load_state<k>(U, v.ld, i, U_i);
-      load_state<np>(prec, v.ld, i, prec_i);
-      indicator.reset(prm, prec_i, U_i);
-    }
-
-    for (uint32_t col = w; col < len; col += W) {
-      const uint32_t e = base + col * 32;
-      const uint32_t j = v.cols[e];
-      double U_j[k], prec_j[np], aux_j[na], c_ij[dim];
-      load_state<k>(U, v.ld, j, U_j);
-      load_state<np>(prec, v.ld, j, prec_j);
-      load_state<na>(aux, v.ld, j, aux_j);
-#pragma unroll
-      for (int d = 0; d < dim; ++d)
-        c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
-      indicator.left = 0.;
-#pragma unroll
-      for (int q = 0; q < k; ++q)
-        indicator.right[q] = 0.;
-      indicator.accumulate(prm, U_i, prec_i, U_j, prec_j, Eq::load_aux(aux_j), c_ij);
-      double *slot = contribution + size_t(col) * (k + 1) * 32 + lane;
-      slot[0] = indicator.left;
-#pragma unroll
-      for (int q = 0; q < k; ++q)
-        slot[(1 + q) * 32] = indicator.right[q];
-    }
-    __syncthreads();
-
-    if (w == 0 && has_row) {
-      indicator.left = 0.;
-#pragma unroll
-      for (int q = 0; q < k; ++q)
-        indicator.right[q] = 0.;
-      for (uint32_t col = 0; col < len; ++col) {
-        const double *slot = contribution + size_t(col) * (k + 1) * 32 + lane;
-        indicator.left += slot[0];
-#pragma unroll
-        for (int q = 0; q < k; ++q)
-          indicator.right[q] += slot[(1 + q) * 32];
-      }
-      const double hd_i = v.mi[i] * v.measure_of_omega_inverse;
-      alpha[i] = indicator.alpha(prm, hd_i);
-    }
-  }
-
-
   /* Step 3a: complete d_ij on coupling boundary pairs (i < j),
    * hyperbolic_module.template.h:461-490. */
   template <class Eq>
@@ -676,11 +562,10 @@ namespace rjb
    * Step 4: low-order update, limiter bounds, r_i and P_ij,
    * hyperbolic_module.template.h:597-884.
    * ---------------------------------------------------------------------- */
-  /* part 0: everything in one sweep.  parts 1 + 2: the same sweep as two lighter kernels,
-   * 1 = low-order update + limiter bounds (no stage states, no alpha), 2 = r_i and P_ij; each
-   * output keeps its accumulation order, the unused half is dead code for the compiler. */
-  template <class Eq, int stages, int part>
-  __global__ void __launch_bounds__(128, Eq::shallow_water ? RJ_MB_LOW_SW : (part == 0 ? RJ_MB_LOW : part == 1 ? RJ_MB_LOW_A : RJ_MB_LOW_B)) k_low_order(StencilView v,
+  /* (Running this sweep as two lighter kernels -- update + bounds, r_i + P_ij -- was measured in
+   * round 1 and rejected: 9.6-11.0 ms instead of 7.0 ms, both halves re-read c_ij, d_ij, U_j.) */
+  template <class Eq, int stages>
+  __global__ void __launch_bounds__(128, Eq::shallow_water ? RJ_MB_LOW_SW : RJ_MB_LOW) k_low_order(StencilView v,
                                                      typename Eq::Params prm,
                                                      uint32_t row_begin,
                                                      uint32_t row_end,
@@ -919,22 +804,17 @@ namespace rjb
         }
       }
 
-      if constexpr (part != 1) {
 #pragma unroll
-        for (int q = 0; q < k; ++q)
-          pij[size_t(q) * v.E_owned + e] = P_ij[q];
-      }
+      for (int q = 0; q < k; ++q)
+        pij[size_t(q) * v.E_owned + e] = P_ij[q];
     }
 
-    if constexpr (part != 1)
-      store_state<k>(r_vec, v.ld, i, F_iH);
-    if constexpr (part != 2) {
-      store_state<k>(U_new, v.ld, i, U_i_new);
-      const double hd_i = m_i * v.measure_of_omega_inverse;
-      double b[nb];
-      limiter.bounds(prm, hd_i, b);
-      store_state<nb>(bounds, v.ld, i, b);
-    }
+    store_state<k>(r_vec, v.ld, i, F_iH);
+    store_state<k>(U_new, v.ld, i, U_i_new);
+    const double hd_i = m_i * v.measure_of_omega_inverse;
+    double b[nb];
+    limiter.bounds(prm, hd_i, b);
+    store_state<nb>(bounds, v.ld, i, b);
   }
 
 
@@ -976,76 +856,6 @@ namespace rjb
     for (uint32_t col = 1; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
       const uint32_t j = RJ_INDEX(RJ_PREFETCH_PIJ, j_next, v.cols, e, col, r.len);
-      double P_ij[k], F_jH[k];
-#pragma unroll
-      for (int q = 0; q < k; ++q)
-        P_ij[q] = pij[size_t(q) * v.E_owned + e];
-      load_state<k>(r_vec, v.ld, j, F_jH);
-
-      const double m_j_inv = v.mi_inv[j];
-      const double m_ij = v.mij[e];
-      const double b_ij = 0. - m_ij * m_j_inv;
-      const double b_ji = 0. - m_ij * m_i_inv;
-
-#pragma unroll
-      for (int q = 0; q < k; ++q) {
-        P_ij[q] += b_ij * F_jH[q] - b_ji * F_iH[q];
-        P_ij[q] *= factor;
-        pij[size_t(q) * v.E_owned + e] = P_ij[q];
-      }
-
-      bool success;
-      const double l_ij = Eq::limit(prm, b, U_i_new, P_ij, success);
-      lij[e] = l_ij;
-      all_ok = all_ok && success;
-    }
-    if (!all_ok)
-      atomicOr(&scalars->restart_needed, 1);
-  }
-
-
-  /* Experimental alternative to k_pij_lij (RJ_PIJ_EDGE=1): the entries of a row are independent
-   * in this sweep (P_ij correction and l_ij = limit(...) per entry, one OR-reduced flag), so a
-   * block of W warps shares the 32 rows of a slice, warp w taking columns w, w+W, ...: W times more
-   * loads in flight per row, same bytes, same arithmetic per entry. */
-  template <class Eq, int W>
-  __global__ void __launch_bounds__(32 * W, RJ_MB_PIJ_EDGE) k_pij_lij_edge(StencilView v,
-                                                                         typename Eq::Params prm,
-                                                                         uint32_t slice_begin,
-                                                                         uint32_t slice_end,
-                                                                         const double *__restrict__ U_new,
-                                                                         const double *__restrict__ r_vec,
-                                                                         const double *__restrict__ bounds,
-                                                                         StepScalars *__restrict__ scalars,
-                                                                         double *__restrict__ pij,
-                                                                         double *__restrict__ lij)
-  {
-    constexpr int k = Eq::k, nb = Eq::n_bounds;
-    const uint32_t g = slice_begin + blockIdx.x;
-    if (g >= slice_end)
-      return;
-    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const uint32_t i = (g << 5) + lane;
-    if (i >= v.n_owned)
-      return;
-    const uint32_t len = v.row_length[i];
-    if (len <= 1)
-      return;
-    const uint32_t base = v.slice_offsets[g] + lane;
-    const double tau = scalars->tau;
-
-    double b[nb], U_i_new[k], F_iH[k];
-    load_state<nb>(bounds, v.ld, i, b);
-    load_state<k>(U_new, v.ld, i, U_i_new);
-    load_state<k>(r_vec, v.ld, i, F_iH);
-    const double m_i_inv = v.mi_inv[i];
-    const double lambda_inv = double(len - 1);
-    const double factor = tau * m_i_inv * lambda_inv;
-
-    bool all_ok = true;
-    for (uint32_t col = 1 + w; col < len; col += W) {
-      const uint32_t e = base + col * 32;
-      const uint32_t j = v.cols[e];
       double P_ij[k], F_jH[k];
 #pragma unroll
       for (int q = 0; q < k; ++q)
@@ -1127,89 +937,6 @@ namespace rjb
 #pragma unroll
       for (int q = 0; q < k; ++q)
         new_p_ij[q] = (1. - old_l_ij) * pij[size_t(q) * v.E_owned + e];
-      bool success;
-      const double new_l_ij = Eq::limit(prm, b, U_i_new, new_p_ij, success);
-      lij_next[e] = (1. - old_l_ij) * new_l_ij;
-    }
-  }
-
-
-  /* Experimental alternative to k_high_order<Eq, false> (RJ_HO_EDGE=1).  A block of W warps owns
-   * one slice of 32 rows:
-   *   phase 1  every warp loads its columns' P_ij (k components) and symmetrised l_ij ONCE into
-   *            shared memory (MAXCOL * (k+1) * 32 doubles = 41.5 kB for 3D Euler);
-   *   phase 2  warp 0 forms U_i^{n+1} += (l_ij lambda) P_ij in COLUMN ORDER from shared memory --
-   *            the additions of the row-parallel kernel, bit for bit -- and publishes U_i^{n+1};
-   *   phase 3  every warp computes the next l_ij of its columns from the staged values.
-   * P_ij is read from global memory once instead of twice (1080 B/DoF of DRAM traffic, the
-   * difference between the measured 2937 and the algorithmic 1724 B/DoF of the row-parallel
-   * kernel), and 32 instead of 128 rows per block shrink the in-flight footprint. */
-  template <class Eq, int W, int MAXCOL>
-  __global__ void __launch_bounds__(32 * W, RJ_MB_HO_EDGE) k_high_order_edge(StencilView v,
-                                                                          typename Eq::Params prm,
-                                                                          uint32_t slice_begin,
-                                                                          uint32_t slice_end,
-                                                                          const double *__restrict__ bounds,
-                                                                          const double *__restrict__ pij,
-                                                                          const double *__restrict__ lij,
-                                                                          double *__restrict__ lij_next,
-                                                                          double *__restrict__ U_new)
-  {
-    constexpr int k = Eq::k, nb = Eq::n_bounds;
-    __shared__ double staged[MAXCOL * (k + 1) * 32]; /* [col][P_0..P_{k-1}, l][lane] */
-    __shared__ double updated[k * 32];               /* U_i^{n+1} of the slice's rows */
-    const uint32_t g = slice_begin + blockIdx.x;
-    if (g >= slice_end)
-      return; /* the whole block */
-    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const uint32_t i = (g << 5) + lane;
-    const bool has_row = i < v.n_owned && v.row_length[i] > 1;
-    const uint32_t len = has_row ? v.row_length[i] : 0u;
-    const uint32_t base = v.slice_offsets[g] + lane;
-
-    for (uint32_t col = 1 + w; col < len; col += W) {
-      const uint32_t e = base + col * 32;
-      double *slot = staged + size_t(col) * (k + 1) * 32 + lane;
-#pragma unroll
-      for (int q = 0; q < k; ++q)
-        slot[q * 32] = pij[size_t(q) * v.E_owned + e];
-      slot[k * 32] = fmin(lij[e], lij[v.transposed[e]]);
-    }
-    __syncthreads();
-
-    if (w == 0 && has_row) {
-      double U_i_new[k];
-      load_state<k>(U_new, v.ld, i, U_i_new);
-      const double lambda = 1. / double(len - 1);
-      for (uint32_t col = 1; col < len; ++col) {
-        const double *slot = staged + size_t(col) * (k + 1) * 32 + lane;
-        const double ll = slot[k * 32] * lambda;
-#pragma unroll
-        for (int q = 0; q < k; ++q)
-          U_i_new[q] += ll * slot[q * 32];
-      }
-      store_state<k>(U_new, v.ld, i, U_i_new);
-#pragma unroll
-      for (int q = 0; q < k; ++q)
-        updated[q * 32 + lane] = U_i_new[q];
-    }
-    __syncthreads();
-
-    if (!has_row)
-      return;
-    double U_i_new[k], b[nb];
-#pragma unroll
-    for (int q = 0; q < k; ++q)
-      U_i_new[q] = updated[q * 32 + lane];
-    load_state<nb>(bounds, v.ld, i, b);
-    for (uint32_t col = 1 + w; col < len; col += W) {
-      const uint32_t e = base + col * 32;
-      const double *slot = staged + size_t(col) * (k + 1) * 32 + lane;
-      const double old_l_ij = slot[k * 32];
-      double new_p_ij[k];
-#pragma unroll
-      for (int q = 0; q < k; ++q)
-        new_p_ij[q] = (1. - old_l_ij) * slot[q * 32];
       bool success;
       const double new_l_ij = Eq::limit(prm, b, U_i_new, new_p_ij, success);
       lij_next[e] = (1. - old_l_ij) * new_l_ij;

@@ -22,13 +22,10 @@ unsigned char *rj_emu_dynamic_smem(); /* tests/host_emulation/host_emulation.cc 
 #endif
 
 #ifndef RJ_TILE_DEFAULT_MASK
-#define RJ_TILE_DEFAULT_MASK 3 /* bit 0: step 5 tiled, bit 1: step 6 tiled, bit 2: fused step 2 (slower: profiles/r2b_variants_tile_kernels.txt) */
+#define RJ_TILE_DEFAULT_MASK 3 /* bit 0: step 5 tiled, bit 1: step 6 tiled */
 #endif
 #ifndef RJ_TILE_W
 #define RJ_TILE_W 4 /* warps per slice */
-#endif
-#ifndef RJ_MB_STEP2_TILE
-#define RJ_MB_STEP2_TILE 8 /* blocks of 32 * RJ_TILE_W threads: 64 registers */
 #endif
 #ifndef RJ_MB_PIJ_TILE
 #define RJ_MB_PIJ_TILE 5
@@ -54,12 +51,6 @@ namespace rjb
     return tile_header_bytes + size_t(width) * 32 * size_t(Eq::k + 1) * 8 + size_t(Eq::k) * 32 * 8;
   }
 
-  template <class Eq>
-  constexpr size_t step2_tile_smem(uint32_t width)
-  {
-    return tile_header_bytes + size_t(width) * 32 * (size_t(Eq::dim) * 8 + 4);
-  }
-
   struct SliceInfo {
     uint32_t g, lane, w, i, len, s0, width, base;
     bool has_row;
@@ -80,121 +71,6 @@ namespace rjb
     if (!s.has_row)
       s.len = 0;
     return s;
-  }
-
-
-  /* ---------------------------------------------------------------------- *
-   * Step 2 on a slice tile: d_ij (j > i) AND alpha_i in one pass over the slice, as the reference
-   * does it (hyperbolic_module.template.h:341-424), instead of the two kernels k_dij + k_alpha that
-   * each stream cols and c_ij from HBM.  The slice's c_ij (dim components) and column indices are
-   * staged by bulk copies; the W warps then specialise:
-   *   warp 0      accumulates the entropy-viscosity indicator over ALL columns of its rows, in
-   *               column order in one thread (the reference's order, bit for bit), writes alpha_i,
-   *               and then joins the others;
-   *   all warps   share the upper-triangle columns (j > i) of every row round-robin, one
-   *               two-state Riemann solve per column, and mirror d_ij into the transposed slot.
-   * No reduction crosses a thread, so no staging of partial sums is needed.
-   * ---------------------------------------------------------------------- */
-  template <class Eq, int W>
-  __global__ void __launch_bounds__(32 * W, RJ_MB_STEP2_TILE) k_step2_tile(StencilView v,
-                                                                         typename Eq::Params prm,
-                                                                         uint32_t slice_begin,
-                                                                         uint32_t slice_end,
-                                                                         uint32_t max_width,
-                                                                         const double *__restrict__ U,
-                                                                         const double *__restrict__ prec,
-                                                                         const double *__restrict__ aux,
-                                                                         double *__restrict__ dij,
-                                                                         double *__restrict__ alpha)
-  {
-    constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec, na = Eq::n_aux;
-    RJ_DYNAMIC_SMEM(smem);
-    const uint32_t g = slice_begin + blockIdx.x;
-    if (g >= slice_end)
-      return; /* the whole block */
-    tile::Barrier *bar = reinterpret_cast<tile::Barrier *>(smem);
-    const uint32_t tile_entries = max_width * 32;
-    double *Cij = reinterpret_cast<double *>(smem + tile_header_bytes);          /* [dim][width][32] */
-    uint32_t *C = reinterpret_cast<uint32_t *>(Cij + size_t(dim) * tile_entries); /* column indices */
-
-    const SliceInfo s = slice_info(v, g);
-    const uint32_t bytes = s.width * 256;
-
-    if (threadIdx.x == 0) {
-      tile::init(bar, 1);
-      tile::fence_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      tile::arrive_expect(bar, dim * bytes + bytes / 2);
-#pragma unroll
-      for (int d = 0; d < dim; ++d)
-        tile::load(Cij + size_t(d) * tile_entries, v.cij + size_t(d) * v.E_owned + s.s0, bytes, bar);
-      tile::load(C, v.cols + s.s0, bytes / 2, bar);
-    }
-
-    double U_i[k], prec_i[np];
-    if (s.has_row) {
-      load_state<k>(U, v.ld, s.i, U_i);
-      load_state<np>(prec, v.ld, s.i, prec_i);
-    }
-
-    tile::wait(bar, 0);
-    if (!s.has_row)
-      return;
-
-    if (s.w == 0) {
-      typename Eq::Indicator indicator;
-      indicator.reset(prm, prec_i, U_i);
-      for (uint32_t col = 0; col < s.len; ++col) {
-        const uint32_t t = col * 32 + s.lane;
-        const uint32_t j = C[t];
-        double U_j[k], prec_j[np], aux_j[na], c_ij[dim];
-        load_state<k>(U, v.ld, j, U_j);
-        load_state<np>(prec, v.ld, j, prec_j);
-        load_state<na>(aux, v.ld, j, aux_j);
-#pragma unroll
-        for (int d = 0; d < dim; ++d)
-          c_ij[d] = Cij[size_t(d) * tile_entries + t];
-        indicator.accumulate(prm, U_i, prec_i, U_j, prec_j, Eq::load_aux(aux_j), c_ij);
-      }
-      const double hd_i = v.mi[s.i] * v.measure_of_omega_inverse;
-      alpha[s.i] = indicator.alpha(prm, hd_i);
-    }
-
-    uint32_t upper = 0; /* running number of the row's upper-triangle columns */
-    for (uint32_t col = 1; col < s.len; ++col) {
-      const uint32_t t = col * 32 + s.lane;
-      const uint32_t j = C[t];
-      if (j < s.i)
-        continue;
-      if ((++upper) % W != s.w)
-        continue;
-      double U_j[k], prec_j[np], c_ij[dim];
-      load_state<k>(U, v.ld, j, U_j);
-      load_state<np>(prec, v.ld, j, prec_j);
-#pragma unroll
-      for (int d = 0; d < dim; ++d)
-        c_ij[d] = Cij[size_t(d) * tile_entries + t];
-
-      double nrm2 = c_ij[0] * c_ij[0];
-#pragma unroll
-      for (int d = 1; d < dim; ++d)
-        nrm2 += c_ij[d] * c_ij[d];
-      const double nrm = sqrt(nrm2);
-      const double inv = 1. / nrm;
-      double n_ij[dim];
-#pragma unroll
-      for (int d = 0; d < dim; ++d)
-        n_ij[d] = c_ij[d] * inv;
-      const double lambda_max = Eq::riemann_lambda_max(prm, U_i, prec_i, U_j, prec_j, n_ij);
-      const double d_ij = nrm * lambda_max;
-      const uint32_t e = s.base + col * 32;
-      dij[e] = d_ij;
-      const uint32_t eT = v.transposed[e];
-      if (eT < v.E_owned)
-        dij[eT] = d_ij;
-    }
   }
 
 
@@ -345,7 +221,7 @@ namespace rjb
     /* the transposed entries l_ji are scattered: the threads gather them while the tiles are in
      * flight (fully unrolled: the values stay in registers); rows longer than the unrolled part
      * gather the rest after the wait */
-    constexpr int n_prefetch = (RJ_ALPHA_EDGE_MAXCOL - 1 + W - 1) / W;
+    constexpr int n_prefetch = (RJ_TILE_PREFETCH_MAXCOL - 1 + W - 1) / W;
     double l_ji[n_prefetch];
 #pragma unroll
     for (int n = 0; n < n_prefetch; ++n) {

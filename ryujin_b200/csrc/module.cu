@@ -683,13 +683,7 @@ namespace rjb
                     bounds,
                     pij);
       };
-#if RJ_SPLIT_LOW
-      if constexpr (!Eq::shallow_water) {
-        run(k_low_order<Eq, 0, 1>, StagePointers<0>{});
-        run(k_low_order<Eq, stages, 2>, st);
-      } else
-#endif
-        run(k_low_order<Eq, stages, 0>, st);
+        run(k_low_order<Eq, stages>, st);
     }
 
     /* hyperbolic_module.template.h:236-1211.
@@ -740,34 +734,15 @@ namespace rjb
       launch(k_reset_scalars, 1, 1, scalars);
 
       /* Step 2: d_ij (j > i), alpha_i; then C3 */
-      const bool step2_tiled = (tile_mask & 4) != 0;
-      if (!step2_tiled) {
-        tag(P_DIJ);
+      tag(P_DIJ);
+      {
         constexpr int W = RJ_DIJ_W; /* warps per slice in the edge-parallel d_ij kernel */
         launch(k_dij<Eq, W>, size_t(od->n_slices) * 32 * W, 32 * W, v, prm, 0u, od->n_slices, old_state.U, old_state.prec, dij);
       }
       sweep(
           [&](uint32_t b, uint32_t e) {
             tag(P_ALPHA);
-            if (step2_tiled) {
-              /* one pass: d_ij and alpha_i of the slices [b / 32, e / 32) */
-              tag(P_DIJ);
-              constexpr int W = RJ_TILE_W;
-              const uint32_t s0 = b / 32, s1 = (e + 31) / 32; /* b is slice aligned */
-              if (s1 > s0)
-                launch_tile(k_step2_tile<Eq, W>, s1 - s0, 32 * W, step2_tile_smem<Eq>(max_row_length), v, prm, s0, s1,
-                            max_row_length, old_state.U, old_state.prec, old_state.aux, dij, alpha);
-            } else
-#if RJ_ALPHA_EDGE
-            if (max_row_length <= RJ_ALPHA_EDGE_MAXCOL) {
-              constexpr int W = RJ_ALPHA_EDGE_W;
-              const uint32_t s0 = b / 32, s1 = (e + 31) / 32; /* b is slice aligned */
-              if (s1 > s0)
-                launch(k_alpha_edge<Eq, W, RJ_ALPHA_EDGE_MAXCOL>, size_t(s1 - s0) * 32 * W, 32 * W, v, prm, s0, s1,
-                       old_state.U, old_state.prec, old_state.aux, alpha);
-            } else
-#endif
-              launch_rows(k_alpha<Eq>, b, e, v, prm, b, e, old_state.U, old_state.prec, old_state.aux, alpha);
+            launch_rows(k_alpha<Eq>, b, e, v, prm, b, e, old_state.U, old_state.prec, old_state.aux, alpha);
             if (e == n_owned && (b < e || b == 0)) {
               /* Step 3: boundary d_ij, d_ii, tau_max (need d_ij only) */
               tag(P_BOUNDARY_DIJ);
@@ -834,17 +809,7 @@ namespace rjb
                               max_row_length, new_state.U, r, bounds, scalars, pij, lij);
                 return;
               }
-#if RJ_PIJ_EDGE
-              {
-                constexpr int W = RJ_PIJ_EDGE_W;
-                const uint32_t s0 = b / 32, s1 = (e + 31) / 32;
-                if (s1 > s0)
-                  launch(k_pij_lij_edge<Eq, W>, size_t(s1 - s0) * 32 * W, 32 * W, v, prm, s0, s1, new_state.U, r, bounds,
-                         scalars, pij, lij);
-              }
-#else
               launch_rows(k_pij_lij<Eq>, b, e, v, prm, b, e, new_state.U, r, bounds, scalars, pij, lij);
-#endif
             },
             [&] { exchange_matrix(lij); });
 
@@ -868,15 +833,6 @@ namespace rjb
                                 s0, s1, max_row_length, bounds, pij, lij, lij_next, new_state.U);
                   return;
                 }
-#if RJ_HO_EDGE
-                if (max_row_length <= RJ_ALPHA_EDGE_MAXCOL) {
-                  constexpr int W = RJ_HO_EDGE_W;
-                  const uint32_t s0 = b / 32, s1 = (e + 31) / 32;
-                  if (s1 > s0)
-                    launch(k_high_order_edge<Eq, W, RJ_ALPHA_EDGE_MAXCOL>, size_t(s1 - s0) * 32 * W, 32 * W, v, prm, s0, s1,
-                           bounds, pij, lij, lij_next, new_state.U);
-                } else
-#endif
                   launch_rows(k_high_order<Eq, false>, b, e, v, prm, b, e, bounds, pij, lij, lij_next, new_state.U);
               },
               [&] { exchange_matrix(lij_next); });

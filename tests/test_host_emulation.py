@@ -71,13 +71,12 @@ def run_fuzz(script, seed, cases, order=""):
 
 def test_fuzz_euler_kernels_against_the_oracle():
     """random meshes (masked, dim 1-3), random boundary ids, 1e6 contrasts: every intermediate of
-    one update and the states after step<0>, step<1> (tests/fuzz/fuzz_euler.py).  The residual is
-    rj_pow vs libm pow (0.03 % of calls differ by one ulp)."""
+    one update and the states after step<0>, step<1> (tests/fuzz/fuzz_euler.py).  Kernel source and
+    oracle execute the same IEEE operations in the same order, with the same pow (the reference's
+    VCL; libm-rounded where the reference itself calls std::pow): bit-identical under the emulation."""
     build()
     worst = run_fuzz("fuzz_euler.py", 11, 16)
-    assert worst["tau"] <= 1e-14 and worst["dij"] <= 1e-14 and worst["alpha"] <= 1e-13
-    assert worst["bounds"] <= 1e-13 and worst["r"] <= 1e-12 and worst["U1"] <= 1e-12 and worst["U2"] <= 1e-11
-    assert worst["counters"] == 0.0
+    assert all(v == 0.0 for v in worst.values()), worst
 
 
 def test_fuzz_shallow_water_kernels_against_the_oracle():
