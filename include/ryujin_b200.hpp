@@ -176,7 +176,7 @@ namespace ryujin_b200
     TimeIntegrator &operator=(const TimeIntegrator &) = delete;
 
     /** Number step(StateVector &state_vector, Number t, Number t_final) */
-    double step(StateVector &state_vector, double t, double t_final = -1.)
+    double step(StateVector &state_vector, double t, double t_final = std::numeric_limits<double>::max())
     {
       double tau = 0.;
       check(rj_time_integrator_step(handle_, state_vector.handle(), t, t_final, &tau));
