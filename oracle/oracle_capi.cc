@@ -7,6 +7,7 @@
 #include "orc_euler.h"
 #include "orc_integrator.h"
 #include "orc_mesh.h"
+#include "orc_mesh_quads.h"
 #include "orc_module.h"
 #include "orc_sparsity.h"
 
@@ -808,6 +809,42 @@ void *orc_offline_from_arrays(int dim,
       run(std::integral_constant<int, 2>());
     else
       run(std::integral_constant<int, 3>());
+  });
+  return rc == 0 ? result : nullptr;
+}
+
+/* General mapped Q1 quadrilateral mesh in 2D (orc_mesh_quads.h): vertices (x, y), cells as 4 vertex
+ * indices in deal.II's lexicographic local order, boundary faces (a, b, id, flip) in deal.II's
+ * visiting order; outward normal of a -> b = (dy, -dx) / |ab|, reversed if flip. */
+void *orc_offline_assemble_quads(unsigned int n_vertices,
+                                 const double *xy,
+                                 unsigned int n_cells,
+                                 const unsigned int *cell_vertices,
+                                 unsigned int n_boundary_faces,
+                                 const unsigned int *face_vertices,
+                                 const unsigned char *face_flip,
+                                 const int *face_ids)
+{
+  void *result = nullptr;
+  const int rc = guarded([&] {
+    QuadMesh mesh;
+    mesh.vertices.resize(n_vertices);
+    for (unsigned int v = 0; v < n_vertices; ++v)
+      mesh.vertices[v] = {xy[2 * v], xy[2 * v + 1]};
+    mesh.cells.resize(n_cells);
+    for (unsigned int c = 0; c < n_cells; ++c)
+      for (int v = 0; v < 4; ++v) {
+        if (cell_vertices[4 * c + v] >= n_vertices)
+          throw std::runtime_error("orc_offline_assemble_quads: vertex index out of range");
+        mesh.cells[c][v] = cell_vertices[4 * c + v];
+      }
+    mesh.boundary_faces.resize(n_boundary_faces);
+    for (unsigned int f = 0; f < n_boundary_faces; ++f)
+      mesh.boundary_faces[f] = {face_vertices[2 * f], face_vertices[2 * f + 1], face_ids[f], face_flip && face_flip[f] != 0};
+    auto *holder = new OfflineHolder<2>();
+    holder->od = assemble_offline_data_quads(mesh);
+    holder->has_mesh = false;
+    result = static_cast<OfflineBase *>(holder);
   });
   return rc == 0 ? result : nullptr;
 }

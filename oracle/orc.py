@@ -286,6 +286,22 @@ class Oracle:
             raise OracleError(self.lib.orc_last_error().decode())
         return Offline(self, handle, dim)
 
+    def assemble_quads(self, vertices, cells, boundary_faces, boundary_flip, boundary_ids):
+        """mapped Q1 quadrilateral mesh (orc_mesh_quads.h): vertices (n, 2); cells (m, 4) vertex indices in
+        deal.II's lexicographic local order; boundary faces (f, 2) in deal.II's visiting order, outward
+        normal of a -> b = (dy, -dx) / |ab|, reversed where boundary_flip is set"""
+        xy = np.ascontiguousarray(vertices, dtype=np.float64)
+        cl = np.ascontiguousarray(cells, dtype=np.uint32)
+        bf = np.ascontiguousarray(boundary_faces, dtype=np.uint32)
+        bi = np.ascontiguousarray(boundary_ids, dtype=np.int32)
+        fl = np.ascontiguousarray(boundary_flip, dtype=np.uint8)
+        self.lib.orc_offline_assemble_quads.restype = C.c_void_p
+        handle = self.lib.orc_offline_assemble_quads(C.c_uint(len(xy)), _dp(xy), C.c_uint(len(cl)), _up(cl), C.c_uint(len(bf)),
+                                                     _up(bf), fl.ctypes.data_as(C.POINTER(C.c_ubyte)), _ip(bi))
+        if not handle:
+            raise OracleError(self.lib.orc_last_error().decode())
+        return Offline(self, handle, 2)
+
     def offline_from_arrays(self, dim, row_ptr, cols, mij, cij, mi, measure, b_index, b_normal, b_id, b_position, pairs):
         rp = np.ascontiguousarray(row_ptr, dtype=np.uint32)
         cl = np.ascontiguousarray(cols, dtype=np.uint32)

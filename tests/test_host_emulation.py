@@ -22,7 +22,8 @@ EMU_LIB = os.path.join(EMU_DIR, "libryujin_b200_hostemu.so")
 
 # minutes-long on one host thread (66k..450k DoFs for hundreds of updates): left to the GPU
 HEAVY = ("conservation_and_symmetry or config1 or vortex_3d_cycles or golden_on_gpu "
-         "or verification_goldens or decks_reproduce")
+         "or verification_goldens or decks_reproduce or config2_vortex or benchmark_size or config5_dam "
+         "or non_fma_build or device_path_equals_host or cylinder_o_grid")
 
 
 def build():
