@@ -411,6 +411,17 @@ int rj_hyperbolic_module_set_profiling(rj_hyperbolic_module *hm, int on);
 int rj_hyperbolic_module_get_profile(rj_hyperbolic_module *hm, double ms[RJ_N_PROFILE_SLOTS], uint64_t counts[RJ_N_PROFILE_SLOTS]);
 
 /* ------------------------------------------------------------------------ *
+ * Postprocessor (source/postprocessor.h, postprocessor.template.h:113-281) on the device: the
+ * schlieren quantity |sum_j c_ij q_j| / m_i of conserved component `first_component` (mode 0) or
+ * the vorticity -- curl -- of the vector quantity starting at `first_component` (mode 1; the
+ * momentum: 1), normalised like the reference: bounds over all ranks (NCCL), then
+ * copysign(1 - exp(-beta ratio), q).  host_out: n_owned values in local row order;
+ * bounds_out (optional): {q_max, q_min} before the normalisation.
+ * ------------------------------------------------------------------------ */
+int rj_postprocessor_compute(rj_hyperbolic_module *hm, const rj_state *state, int mode, int first_component, double beta,
+                             double *host_out, double *bounds_out);
+
+/* ------------------------------------------------------------------------ *
  * TimeIntegrator (source/time_integrator.h, .template.h:207-443): host-side
  * driver kept so that callers of TimeIntegrator::step() are drop-in.
  * ------------------------------------------------------------------------ */

@@ -466,6 +466,68 @@ namespace
 } // namespace
 
 
+namespace
+{
+  template <int D>
+  void postprocess_impl(const OfflineData<D> &od, int k, const double *U, int mode, int first, double beta, double *out, double *bounds)
+  {
+      
+  const unsigned int n = od.n_owned;
+  for (unsigned int i = 0; i < n; ++i) {
+    out[i] = 0.;
+    const unsigned int row_length = od.row_length(i);
+    if (row_length == 1)
+      continue;
+    double acc[3] = {0., 0., 0.};
+    for (unsigned int col_idx = 0; col_idx < row_length; ++col_idx) {
+      const std::size_t e = od.row_ptr[i] + col_idx;
+      const unsigned int j = od.cols[e];
+      const auto c_ij = od.c(e);
+      if (mode == 0) {
+        const double q_j = U[std::size_t(j) * k + first];
+        for (int d = 0; d < D; ++d)
+          acc[d] -= c_ij[d] * q_j;
+      } else {
+        double q_j[3] = {0., 0., 0.};
+        for (int d = 0; d < D; ++d)
+          q_j[d] = U[std::size_t(j) * k + first + d];
+        if (D == 2)
+          acc[0] -= c_ij[D - 1] * q_j[0] - c_ij[0] * q_j[D - 1];
+        else if (D == 3) {
+          acc[0] -= c_ij[1 % D] * q_j[2 % D] - c_ij[2 % D] * q_j[1 % D];
+          acc[1] -= c_ij[2 % D] * q_j[0] - c_ij[0] * q_j[2 % D];
+          acc[2] -= c_ij[0] * q_j[1 % D] - c_ij[1 % D] * q_j[0];
+        }
+      }
+    }
+    const double m_i = od.mi[i];
+    if (mode == 1 && D == 2)
+      out[i] = acc[0] / m_i;
+    else {
+      double n2 = acc[0] * acc[0];
+      const int n_acc = mode == 0 ? D : 3;
+      for (int d = 1; d < n_acc; ++d)
+        n2 += acc[d] * acc[d];
+      out[i] = std::sqrt(n2) / m_i;
+    }
+  }
+  double q_max = 0., q_min = max_double;
+  for (unsigned int i = 0; i < n; ++i) {
+    q_max = std::max(q_max, std::abs(out[i]));
+    q_min = std::min(q_min, std::abs(out[i]));
+  }
+  bounds[0] = q_max;
+  bounds[1] = q_min;
+  const double floor = std::max(1.0e-10, eps_double);
+  for (unsigned int i = 0; i < n; ++i) {
+    const double q = out[i];
+    const double ratio = std::max(0., std::abs(q) - q_min - floor) / std::max(q_max - q_min, eps_double);
+    const double magnitude = 1. - std::exp(-beta * ratio);
+    out[i] = std::copysign(magnitude, q);
+  }
+  }
+} // namespace
+
 extern "C" {
 
 const char *orc_last_error() { return last_error.c_str(); }
@@ -872,7 +934,19 @@ void orc_offline_destroy(void *h) { delete static_cast<OfflineBase *>(h); }
     }                                                                          \
   } while (0)
 
+
+int orc_postprocess(void *h, int k, const double *U, int mode, int first, double beta, double *out, double *bounds)
+{
+  return guarded([&] {
+    WITH_OFFLINE(h, { postprocess_impl<D>(H.od, k, U, mode, first, beta, out, bounds); });
+    return 0;
+  });
+}
+
 /* sizes: out = (n_dofs, nnz, n_boundary, n_pairs) */
+/* Postprocessor::compute for one quantity (source/postprocessor.template.h:113-281): mode 0 schlieren
+ * of component `first`, mode 1 vorticity of the vector starting at `first`; U is AoS with k components;
+ * out: n values on the exponential scale, bounds: {q_max, q_min}. */
 /* owner rank of every row: N-rank emulation, see OfflineData::partition (orc_module.h) */
 void orc_offline_set_partition(void *h, const int *partition)
 {

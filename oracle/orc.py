@@ -338,6 +338,15 @@ class Offline:
         except Exception:
             pass
 
+    def postprocess(self, U, mode, first, beta=10.0):
+        """Postprocessor::compute for one quantity -> (values on the exponential scale, (q_max, q_min))"""
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        out = np.zeros(self.n)
+        bounds = np.zeros(2)
+        self.o._check(self.o.lib.orc_postprocess(self.h, int(U.shape[1]), _dp(U), int(mode), int(first), C.c_double(beta),
+                                                 _dp(out), _dp(bounds)))
+        return out, (bounds[0], bounds[1])
+
     def set_partition(self, partition):
         """owner rank of every row (N-rank emulation, orc_module.h OfflineData::partition); None
         restores the single-rank semantics"""

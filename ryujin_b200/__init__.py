@@ -15,6 +15,7 @@ from .hyperbolic_module import (  # noqa: F401
     InitialState,
     InitialValues,
     ModuleParameters,
+    Postprocessor,
     StateVector,
     Stepping,
     TimeIntegrator,

@@ -214,6 +214,7 @@ _SIGNATURES = {
     "rj_hyperbolic_module_kernel_launches": (C.c_uint64, [vp]),
     "rj_hyperbolic_module_set_profiling": (C.c_int, [vp, C.c_int]),
     "rj_hyperbolic_module_get_profile": (C.c_int, [vp, f64p, u64p]),
+    "rj_postprocessor_compute": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_double, f64p, f64p]),
     "rj_time_integrator_create": (C.c_int, [C.POINTER(vp), vp, C.c_int, C.c_double, C.c_double, C.c_int]),
     "rj_time_integrator_destroy": (None, [vp]),
     "rj_time_integrator_step": (C.c_int, [vp, vp, C.c_double, C.c_double, f64p]),

@@ -945,6 +945,108 @@ namespace rjb
 
 
   /* ---------------------------------------------------------------------- *
+   * Postprocessor (source/postprocessor.template.h:113-281): schlieren |sum_j c_ij q_j| / m_i of a
+   * scalar quantity and the vorticity (curl) of a vector quantity, on the exponential scale
+   * 1 - exp(-beta ratio).  Row sums in column order like every other per-row accumulation.
+   * ---------------------------------------------------------------------- */
+  struct PostprocessorScalars {
+    unsigned long long max_bits, min_bits; /* ordered bit patterns of |q| >= 0 */
+    double q_max, q_min;
+  };
+
+  __global__ void k_postprocess_reset(PostprocessorScalars *s)
+  {
+    s->max_bits = 0ull;
+    s->min_bits = (unsigned long long)__double_as_longlong(DBL_MAX);
+    s->q_max = 0.;
+    s->q_min = DBL_MAX;
+  }
+
+  /* mode 0: schlieren of component `first`; mode 1: vorticity of components first .. first+dim-1 */
+  template <int dim>
+  __global__ void k_postprocess_quantity(StencilView v,
+                                         uint32_t row_begin,
+                                         uint32_t row_end,
+                                         int mode,
+                                         uint32_t first,
+                                         const double *__restrict__ U,
+                                         double *__restrict__ quantity,
+                                         PostprocessorScalars *__restrict__ scalars)
+  {
+    RowInfo r;
+    double value = 0.;
+    bool active = false;
+    if (row_info(v, row_begin, row_end, r) && r.len > 1) {
+      active = true;
+      double acc[3] = {0., 0., 0.};
+      for (uint32_t col = 0; col < r.len; ++col) {
+        const uint32_t e = r.base + col * 32;
+        const uint32_t j = v.cols[e];
+        double c_ij[dim];
+#pragma unroll
+        for (int d = 0; d < dim; ++d)
+          c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
+        if (mode == 0) {
+          const double q_j = U[size_t(first) * v.ld + j];
+#pragma unroll
+          for (int d = 0; d < dim; ++d)
+            acc[d] -= c_ij[d] * q_j;
+        } else {
+          double q_j[dim];
+#pragma unroll
+          for (int d = 0; d < dim; ++d)
+            q_j[d] = U[size_t(first + d) * v.ld + j];
+          if (dim == 2) {
+            /* cross_product_2d(c_ij) * q_j = (c_y, -c_x) . q */
+            acc[0] -= c_ij[dim - 1] * q_j[0] - c_ij[0] * q_j[dim - 1];
+          } else if (dim == 3) {
+            acc[0] -= c_ij[1 % dim] * q_j[2 % dim] - c_ij[2 % dim] * q_j[1 % dim];
+            acc[1] -= c_ij[2 % dim] * q_j[0] - c_ij[0] * q_j[2 % dim];
+            acc[2] -= c_ij[0] * q_j[1 % dim] - c_ij[1 % dim] * q_j[0];
+          }
+        }
+      }
+      const double m_i = v.mi[r.i];
+      if (mode == 1 && dim == 2)
+        value = acc[0] / m_i;
+      else {
+        double n2 = acc[0] * acc[0];
+        const int n_acc = mode == 0 ? dim : 3;
+        for (int d = 1; d < n_acc; ++d)
+          n2 += acc[d] * acc[d];
+        value = sqrt(n2) / m_i;
+      }
+      quantity[r.i] = value;
+    } else if (r.i < row_end)
+      quantity[r.i] = 0.;
+    /* bounds over all owned rows (constrained rows hold 0) */
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(active ? value : 0.));
+    if (r.i < row_end) {
+      atomicMax(&scalars->max_bits, bits);
+      atomicMin(&scalars->min_bits, bits);
+    }
+  }
+
+  __global__ void k_postprocess_bounds(PostprocessorScalars *s)
+  {
+    s->q_max = __longlong_as_double((long long)s->max_bits);
+    s->q_min = __longlong_as_double((long long)s->min_bits);
+  }
+
+  __global__ void k_postprocess_normalize(uint32_t n, double beta, const PostprocessorScalars *__restrict__ s, double *__restrict__ quantity)
+  {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+      return;
+    const double floor = fmax(1.0e-10, DBL_EPSILON);
+    const double q = quantity[i];
+    const double ratio = fmax(0., fabs(q) - s->q_min - floor) / fmax(s->q_max - s->q_min, DBL_EPSILON);
+    const double magnitude = 1. - exp(-beta * ratio);
+    quantity[i] = copysign(magnitude, q);
+  }
+
+
+  /* ---------------------------------------------------------------------- *
    * Plumbing kernels
    * ---------------------------------------------------------------------- */
 

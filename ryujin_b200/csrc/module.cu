@@ -1778,6 +1778,57 @@ int rj_hyperbolic_module_get_scratch(rj_hyperbolic_module *hm, int what, double 
   });
 }
 
+/* Postprocessor::compute (source/postprocessor.template.h:113-281) for one quantity */
+int rj_postprocessor_compute(rj_hyperbolic_module *hm, const rj_state *state, int mode, int first_component, double beta,
+                             double *host_out, double *bounds_out)
+{
+  return guarded([&] {
+    if (!hm || !state || !host_out || state->hm != hm)
+      throw InvalidArgument("rj_postprocessor_compute: invalid argument");
+    const int dim = hm->od->dim;
+    if (mode < 0 || mode > 1 || first_component < 0 || first_component + (mode == 1 ? dim : 1) > hm->k)
+      throw InvalidArgument("rj_postprocessor_compute: component out of range");
+    if (mode == 1 && dim < 2)
+      throw InvalidArgument("rj_postprocessor_compute: no vorticity in 1D");
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    hm->cur = hm->stream;
+    const auto *od = hm->od;
+    const uint32_t n = od->n_owned;
+    const StencilView v = hm->view();
+    PostprocessorScalars *ps = nullptr;
+    RJ_CUDA(cudaMalloc(&ps, sizeof(PostprocessorScalars)));
+    double *q = hm->staging; /* n_owned doubles */
+    try {
+      hm->launch(k_postprocess_reset, 1, 1, ps);
+      if (dim == 1)
+        hm->launch(k_postprocess_quantity<1>, n, 128, v, 0u, n, mode, uint32_t(first_component), state->U, q, ps);
+      else if (dim == 2)
+        hm->launch(k_postprocess_quantity<2>, n, 128, v, 0u, n, mode, uint32_t(first_component), state->U, q, ps);
+      else
+        hm->launch(k_postprocess_quantity<3>, n, 128, v, 0u, n, mode, uint32_t(first_component), state->U, q, ps);
+      hm->launch(k_postprocess_bounds, 1, 1, ps);
+      if (hm->comm && hm->comm->n_ranks > 1) {
+        RJ_NCCL(ncclAllReduce(&ps->q_max, &ps->q_max, 1, ncclDouble, ncclMax, hm->comm->comm, hm->stream));
+        RJ_NCCL(ncclAllReduce(&ps->q_min, &ps->q_min, 1, ncclDouble, ncclMin, hm->comm->comm, hm->stream));
+      }
+      hm->launch(k_postprocess_normalize, n, 256, n, beta, (const PostprocessorScalars *)ps, q);
+      RJ_CUDA(cudaMemcpyAsync(host_out, q, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, hm->stream));
+      PostprocessorScalars h{};
+      RJ_CUDA(cudaMemcpyAsync(&h, ps, sizeof(h), cudaMemcpyDeviceToHost, hm->stream));
+      RJ_CUDA(cudaStreamSynchronize(hm->stream));
+      if (bounds_out) {
+        bounds_out[0] = h.q_max;
+        bounds_out[1] = h.q_min;
+      }
+    } catch (...) {
+      cudaFree(ps);
+      throw;
+    }
+    RJ_CUDA(cudaFree(ps));
+    return RJ_OK;
+  });
+}
+
 /* ---- state vectors ---- */
 
 int rj_state_create(rj_state **out, rj_hyperbolic_module *hm)

@@ -331,6 +331,37 @@ class HyperbolicModule:
             self._h = None
 
 
+class Postprocessor:
+    """Postprocessor (source/postprocessor.h): schlieren and vorticity plots of a state vector on
+    the exponential scale, computed on the device.  Parameters as in the reference's prm section
+    ("schlieren beta" = 10, "schlieren quantities" = [rho], "vorticity quantities" = [])."""
+
+    def __init__(self, module, schlieren_beta=10.0, schlieren_quantities=("rho",), vorticity_quantities=()):
+        self.module = module
+        self.beta = float(schlieren_beta)
+        names = ["rho"] + ["m_%d" % (d + 1) for d in range(module.offline_data.dim)] + ["E"]
+        if module.k == module.offline_data.dim + 1:  # shallow water: (h, m)
+            names = ["h"] + ["m_%d" % (d + 1) for d in range(module.offline_data.dim)]
+        self._index = {name: q for q, name in enumerate(names)}
+        self._index["m"] = 1
+        self.schlieren_quantities = list(schlieren_quantities)
+        self.vorticity_quantities = list(vorticity_quantities)
+        self.bounds = {}
+
+    def compute(self, state):
+        """-> {"schlieren_rho": array(n_owned), "vorticity_m": ...}"""
+        out = {}
+        for mode, prefix, quantities in ((0, "schlieren_", self.schlieren_quantities), (1, "vorticity_", self.vorticity_quantities)):
+            for name in quantities:
+                values = np.zeros(self.module.n_owned)
+                bounds = (C.c_double * 2)()
+                check(lib.rj_postprocessor_compute(self.module._h, state._h, mode, self._index[name], self.beta,
+                                                   values.ctypes.data_as(_lib.f64p), bounds))
+                out[prefix + name] = values
+                self.bounds[prefix + name] = (bounds[0], bounds[1])
+        return out
+
+
 class TimeIntegrator:
     """source/time_integrator.template.h:207-443 (explicit schemes)"""
 

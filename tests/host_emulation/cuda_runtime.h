@@ -155,6 +155,7 @@ inline long long __double_as_longlong(double x) { long long u; std::memcpy(&u, &
 inline double __longlong_as_double(long long u) { double x; std::memcpy(&x, &u, 8); return x; }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { const auto old = *p; if (v < old) *p = v; return old; }
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { const auto old = *p; if (v > old) *p = v; return old; }
 inline int atomicOr(int *p, int v) { const int old = *p; *p = old | v; return old; }
 
 /* ---- block execution engine (host_emulation.cc) ---- */

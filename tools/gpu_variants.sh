@@ -8,9 +8,9 @@ mkdir -p gpurun_out
 for v in ${VARIANT_NAMES:-$(ls gpurun_variants/lib_*.so | sed 's#.*/lib_##; s#\.so$##')}; do
   stem=${v%_tile[0-9]*}
   f=gpurun_variants/lib_$stem.so
-  tile=""
-  case "$v" in *_tile[0-9]*) tile=${v##*_tile};; esac
-  RYUJIN_B200_TILE=$tile RYUJIN_B200_LIB=$PWD/$f python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/var_$v.json 2> gpurun_out/var_$v.err
+  unset RYUJIN_B200_TILE
+  case "$v" in *_tile[0-9]*) export RYUJIN_B200_TILE=${v##*_tile};; esac
+  RYUJIN_B200_LIB=$PWD/$f python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/var_$v.json 2> gpurun_out/var_$v.err
   python - "$v" <<'PY'
 import json, sys
 v = sys.argv[1]
