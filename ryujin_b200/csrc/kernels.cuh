@@ -18,7 +18,7 @@
 /* minimum resident blocks of 128 threads per SM requested from ptxas for the four
  * FP64-heavy kernels (caps registers at 65536 / (128 * MB)); tuned in profiles/ */
 #ifndef RJ_MB_DIJ
-#define RJ_MB_DIJ 8 /* blocks of 32 * RJ_DIJ_W threads: 64 registers */
+#define RJ_MB_DIJ 12 /* blocks of 32 * RJ_DIJ_W threads: 42 registers; r2d: 8 -> 5.29 ms, 10 -> 4.93, 12 -> 4.80 */
 #endif
 #define RJ_PRAGMA_(x) _Pragma(#x)
 #define RJ_PRAGMA(x) RJ_PRAGMA_(x)
@@ -73,7 +73,7 @@
 #define RJ_DIJ_W 4 /* warps per slice of the edge-parallel d_ij kernel */
 #endif
 #ifndef RJ_MB_ALPHA
-#define RJ_MB_ALPHA 6
+#define RJ_MB_ALPHA 8
 #endif
 #ifndef RJ_MB_LOW
 #define RJ_MB_LOW 4
@@ -85,7 +85,7 @@
 #define RJ_MB_PIJ 5
 #endif
 #ifndef RJ_MB_HO
-#define RJ_MB_HO 8
+#define RJ_MB_HO 6
 #endif
 
 namespace rjb
