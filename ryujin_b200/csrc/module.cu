@@ -98,6 +98,11 @@ struct rj_hyperbolic_module {
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
   int dij_blocks_per_sm = RJ_STEP2_CONCURRENT_DEFAULT;
+  /* steps 4 and 5 pipelined over two halves of the rows (single rank): the FP64-issue bound low-order
+   * sweep of the second half runs concurrently with the memory bound P_ij / l_ij sweep of those rows of
+   * the first half that couple to first-half rows only (rows below split - bandwidth).  Same kernels,
+   * same row-local arithmetic: bit-identical.  RYUJIN_B200_PIPELINE=1 */
+  int pipeline = RJ_PIPELINE_DEFAULT;
   cudaStream_t cur = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap = true;
@@ -807,37 +812,52 @@ namespace rjb
       }
       launch(k_tau_finalize, 1, 1, scalars, tau_source, cycle);
 
-      /* Step 4: low-order update, bounds, r_i, P_ij; C6 */
-      sweep(
-          [&](uint32_t b, uint32_t e) {
-            tag(P_LOW_ORDER);
-            switch (stages) {
-            case 0: low_order<0>(b, e, old_state, stage_states, stage_weights, new_state); break;
-            case 1: low_order<1>(b, e, old_state, stage_states, stage_weights, new_state); break;
-            case 2: low_order<2>(b, e, old_state, stage_states, stage_weights, new_state); break;
-            case 3: low_order<3>(b, e, old_state, stage_states, stage_weights, new_state); break;
-            case 4: low_order<4>(b, e, old_state, stage_states, stage_weights, new_state); break;
-            }
-          },
-          [&] { exchange_vector(r, Eq::k); });
-
-      /* Step 5: P_ij correction and first l_ij; C7 */
+      auto low_order_rows = [&](uint32_t b, uint32_t e) {
+        tag(P_LOW_ORDER);
+        switch (stages) {
+        case 0: low_order<0>(b, e, old_state, stage_states, stage_weights, new_state); break;
+        case 1: low_order<1>(b, e, old_state, stage_states, stage_weights, new_state); break;
+        case 2: low_order<2>(b, e, old_state, stage_states, stage_weights, new_state); break;
+        case 3: low_order<3>(b, e, old_state, stage_states, stage_weights, new_state); break;
+        case 4: low_order<4>(b, e, old_state, stage_states, stage_weights, new_state); break;
+        }
+      };
+      auto pij_lij_rows = [&](uint32_t b, uint32_t e) {
+        tag(P_PIJ_LIJ);
+        if (tile_mask & 1) {
+          constexpr int W = RJ_TILE_W;
+          const uint32_t s0 = b / 32, s1 = (e + 31) / 32; /* b is slice aligned */
+          if (s1 > s0)
+            launch_tile(k_pij_lij_tile<Eq, W>, s1 - s0, 32 * W, pij_tile_smem<Eq>(max_row_length), v, prm, s0, s1,
+                        max_row_length, new_state.U, r, bounds, scalars, pij, lij);
+          return;
+        }
+        launch_rows(k_pij_lij<Eq>, b, e, v, prm, b, e, new_state.U, r, bounds, scalars, pij, lij);
+      };
       const unsigned int n_iterations = mp.limiter_iterations;
-      if (n_iterations != 0)
-        sweep(
-            [&](uint32_t b, uint32_t e) {
-              tag(P_PIJ_LIJ);
-              if (tile_mask & 1) {
-                constexpr int W = RJ_TILE_W;
-                const uint32_t s0 = b / 32, s1 = (e + 31) / 32; /* b is slice aligned */
-                if (s1 > s0)
-                  launch_tile(k_pij_lij_tile<Eq, W>, s1 - s0, 32 * W, pij_tile_smem<Eq>(max_row_length), v, prm, s0, s1,
-                              max_row_length, new_state.U, r, bounds, scalars, pij, lij);
-                return;
-              }
-              launch_rows(k_pij_lij<Eq>, b, e, v, prm, b, e, new_state.U, r, bounds, scalars, pij, lij);
-            },
-            [&] { exchange_matrix(lij); });
+      /* rows [0, safe) couple to rows below `split` only */
+      const uint32_t split = ((n_owned / 2) + 31u) & ~31u;
+      const uint32_t safe = split > od->bandwidth ? (split - od->bandwidth) & ~31u : 0u;
+      if (pipeline && !multi && aux_stream && !profiling && n_iterations != 0 && safe >= 64) {
+        /* Steps 4 and 5 as a two-stage pipeline over the two halves of the rows */
+        low_order_rows(0u, split);
+        RJ_CUDA(cudaEventRecord(ev_aux_fork, stream));
+        RJ_CUDA(cudaStreamWaitEvent(aux_stream, ev_aux_fork, 0));
+        cur = aux_stream;
+        pij_lij_rows(0u, safe);
+        RJ_CUDA(cudaEventRecord(ev_aux_join, aux_stream));
+        cur = stream;
+        low_order_rows(split, n_owned);
+        pij_lij_rows(safe, n_owned);
+        RJ_CUDA(cudaStreamWaitEvent(stream, ev_aux_join, 0));
+      } else {
+        /* Step 4: low-order update, bounds, r_i, P_ij; C6 */
+        sweep(low_order_rows, [&] { exchange_vector(r, Eq::k); });
+
+        /* Step 5: P_ij correction and first l_ij; C7 */
+        if (n_iterations != 0)
+          sweep(pij_lij_rows, [&] { exchange_matrix(lij); });
+      }
 
       /* Steps 6, 7; C8 */
       for (unsigned int pass = 0; pass < n_iterations; ++pass) {
@@ -1132,7 +1152,7 @@ namespace rjb
         key.push_back(s->aux);
       }
       key.push_back(reinterpret_cast<const void *>(
-          uintptr_t((hm.overlapping() ? 1u : 0u) | (unsigned(hm.tile_mask) << 1) | (unsigned(hm.dij_blocks_per_sm) << 8))));
+          uintptr_t((hm.overlapping() ? 1u : 0u) | (unsigned(hm.tile_mask) << 1) | (unsigned(hm.dij_blocks_per_sm) << 8) | (unsigned(hm.pipeline) << 16))));
       uint64_t cfl_bits;
       std::memcpy(&cfl_bits, &hm.cfl, sizeof(cfl_bits));
       key.push_back(reinterpret_cast<const void *>(cfl_bits));
@@ -1579,7 +1599,9 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
       hm->overlap = std::string(env) != "0";
     if (const char *env = std::getenv("RYUJIN_B200_STEP2_CONCURRENT"))
       hm->dij_blocks_per_sm = std::atoi(env);
-    if (hm->dij_blocks_per_sm > 0) {
+    if (const char *env = std::getenv("RYUJIN_B200_PIPELINE"))
+      hm->pipeline = std::atoi(env);
+    if (hm->dij_blocks_per_sm > 0 || hm->pipeline) {
       RJ_CUDA(cudaStreamCreateWithFlags(&hm->aux_stream, cudaStreamNonBlocking));
       RJ_CUDA(cudaEventCreateWithFlags(&hm->ev_aux_fork, cudaEventDisableTiming));
       RJ_CUDA(cudaEventCreateWithFlags(&hm->ev_aux_join, cudaEventDisableTiming));
