@@ -127,19 +127,6 @@ namespace rjb
       const uint32_t E_owned = slice_off[od->n_slices];
       od->E_owned = E_owned;
 
-      /* bandwidth of the owned block: max |i - j| */
-      {
-        uint32_t bw = 0;
-#pragma omp parallel for schedule(static) reduction(max : bw)
-        for (uint32_t i = 0; i < n_owned; ++i)
-          for (uint32_t c = 1; c < row_len[i]; ++c) {
-            const uint32_t j = host_column(d, i, c);
-            if (j < n_owned)
-              bw = std::max<uint32_t>(bw, j > i ? j - i : i - j);
-          }
-        od->bandwidth = bw;
-      }
-
       /* ghost rows: for each ghost j the owned neighbours i (ascending) */
       const uint32_t n_ghost = d.n_relevant - d.n_owned;
       std::vector<uint32_t> ghost_row_start(size_t(n_ghost) + 1, 0);

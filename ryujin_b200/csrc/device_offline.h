@@ -76,7 +76,6 @@ struct rj_offline {
    * export-rows-first overlap of the module (violated by e.g. an imported stencil that does not
    * declare its export range: the module then exchanges after the full sweep) */
   bool export_rows_first = true;
-  uint32_t bandwidth = 0; /* max |i - j| over the owned entries: rows below a split minus this couple to rows below the split only */
 
   uint32_t entry(uint32_t row, uint32_t col) const
   {

@@ -24,12 +24,6 @@ unsigned char *rj_emu_dynamic_smem(); /* tests/host_emulation/host_emulation.cc 
 #ifndef RJ_TILE_DEFAULT_MASK
 #define RJ_TILE_DEFAULT_MASK 3 /* bit 0: step 5 tiled, bit 1: step 6 tiled */
 #endif
-#ifndef RJ_STEP2_CONCURRENT_DEFAULT
-#define RJ_STEP2_CONCURRENT_DEFAULT 0 /* resident k_dij blocks per SM when step 2 runs as two concurrent kernels; 0 = sequential */
-#endif
-#ifndef RJ_PIPELINE_DEFAULT
-#define RJ_PIPELINE_DEFAULT 0 /* 1: steps 4 and 5 pipelined over two halves of the rows (single rank) */
-#endif
 #ifndef RJ_TILE_W
 #define RJ_TILE_W 4 /* warps per slice */
 #endif

@@ -90,19 +90,6 @@ struct rj_hyperbolic_module {
    * "fire the exchange once the export rows are done").  `cur` is the stream launch() and the
    * exchanges currently target. */
   cudaStream_t comm_stream = nullptr;
-  /* step 2 as two CONCURRENT kernels: k_dij (FP64-issue bound, little memory traffic) on a second
-   * stream next to k_alpha (gather-latency bound, little FP64) on the main stream -- they are
-   * independent (d_ij / alpha_i from the same U, prec) and stress different units of the SM.
-   * dij_blocks_per_sm > 0 caps the resident k_dij blocks (by a dynamic shared memory reservation)
-   * so that k_alpha blocks find room next to them.  RYUJIN_B200_STEP2_CONCURRENT=<blocks per SM> */
-  cudaStream_t aux_stream = nullptr;
-  cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
-  int dij_blocks_per_sm = RJ_STEP2_CONCURRENT_DEFAULT;
-  /* steps 4 and 5 pipelined over two halves of the rows (single rank): the FP64-issue bound low-order
-   * sweep of the second half runs concurrently with the memory bound P_ij / l_ij sweep of those rows of
-   * the first half that couple to first-half rows only (rows below split - bandwidth).  Same kernels,
-   * same row-local arithmetic: bit-identical.  RYUJIN_B200_PIPELINE=1 */
-  int pipeline = RJ_PIPELINE_DEFAULT;
   cudaStream_t cur = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap = true;
@@ -501,12 +488,7 @@ rj_hyperbolic_module::~rj_hyperbolic_module()
     cudaEventDestroy(ev_join);
   if (comm_stream)
     cudaStreamDestroy(comm_stream);
-  if (ev_aux_fork)
-    cudaEventDestroy(ev_aux_fork);
-  if (ev_aux_join)
-    cudaEventDestroy(ev_aux_join);
-  if (aux_stream)
-    cudaStreamDestroy(aux_stream);
+
   if (owns_stream && stream)
     cudaStreamDestroy(stream);
 }
@@ -754,19 +736,9 @@ namespace rjb
 
       /* Step 2: d_ij (j > i), alpha_i; then C3 */
       tag(P_DIJ);
-      const bool step2_concurrent = dij_blocks_per_sm > 0 && aux_stream && !profiling;
       {
         constexpr int W = RJ_DIJ_W; /* warps per slice in the edge-parallel d_ij kernel */
-        if (step2_concurrent) {
-          RJ_CUDA(cudaEventRecord(ev_aux_fork, stream));
-          RJ_CUDA(cudaStreamWaitEvent(aux_stream, ev_aux_fork, 0));
-          cur = aux_stream;
-          const size_t reserve = std::min<size_t>(200 * 1024, (220 * 1024) / size_t(dij_blocks_per_sm) - 1024);
-          launch_tile(k_dij<Eq, W>, od->n_slices, 32 * W, reserve, v, prm, 0u, od->n_slices, old_state.U, old_state.prec, dij);
-          RJ_CUDA(cudaEventRecord(ev_aux_join, aux_stream));
-          cur = stream;
-        } else
-          launch(k_dij<Eq, W>, size_t(od->n_slices) * 32 * W, 32 * W, v, prm, 0u, od->n_slices, old_state.U, old_state.prec, dij);
+        launch(k_dij<Eq, W>, size_t(od->n_slices) * 32 * W, 32 * W, v, prm, 0u, od->n_slices, old_state.U, old_state.prec, dij);
       }
       sweep(
           [&](uint32_t b, uint32_t e) {
@@ -774,8 +746,6 @@ namespace rjb
             launch_rows(k_alpha<Eq>, b, e, v, prm, b, e, old_state.U, old_state.prec, old_state.aux, alpha);
             if (e == n_owned && (b < e || b == 0)) {
               /* Step 3: boundary d_ij, d_ii, tau_max (need d_ij only) */
-              if (step2_concurrent)
-                RJ_CUDA(cudaStreamWaitEvent(stream, ev_aux_join, 0));
               tag(P_BOUNDARY_DIJ);
               launch(k_boundary_dij<Eq>,
                      od->n_pairs,
@@ -835,29 +805,12 @@ namespace rjb
         launch_rows(k_pij_lij<Eq>, b, e, v, prm, b, e, new_state.U, r, bounds, scalars, pij, lij);
       };
       const unsigned int n_iterations = mp.limiter_iterations;
-      /* rows [0, safe) couple to rows below `split` only */
-      const uint32_t split = ((n_owned / 2) + 31u) & ~31u;
-      const uint32_t safe = split > od->bandwidth ? (split - od->bandwidth) & ~31u : 0u;
-      if (pipeline && !multi && aux_stream && !profiling && n_iterations != 0 && safe >= 64) {
-        /* Steps 4 and 5 as a two-stage pipeline over the two halves of the rows */
-        low_order_rows(0u, split);
-        RJ_CUDA(cudaEventRecord(ev_aux_fork, stream));
-        RJ_CUDA(cudaStreamWaitEvent(aux_stream, ev_aux_fork, 0));
-        cur = aux_stream;
-        pij_lij_rows(0u, safe);
-        RJ_CUDA(cudaEventRecord(ev_aux_join, aux_stream));
-        cur = stream;
-        low_order_rows(split, n_owned);
-        pij_lij_rows(safe, n_owned);
-        RJ_CUDA(cudaStreamWaitEvent(stream, ev_aux_join, 0));
-      } else {
-        /* Step 4: low-order update, bounds, r_i, P_ij; C6 */
-        sweep(low_order_rows, [&] { exchange_vector(r, Eq::k); });
+      /* Step 4: low-order update, bounds, r_i, P_ij; C6 */
+      sweep(low_order_rows, [&] { exchange_vector(r, Eq::k); });
 
-        /* Step 5: P_ij correction and first l_ij; C7 */
-        if (n_iterations != 0)
-          sweep(pij_lij_rows, [&] { exchange_matrix(lij); });
-      }
+      /* Step 5: P_ij correction and first l_ij; C7 */
+      if (n_iterations != 0)
+        sweep(pij_lij_rows, [&] { exchange_matrix(lij); });
 
       /* Steps 6, 7; C8 */
       for (unsigned int pass = 0; pass < n_iterations; ++pass) {
@@ -1152,7 +1105,7 @@ namespace rjb
         key.push_back(s->aux);
       }
       key.push_back(reinterpret_cast<const void *>(
-          uintptr_t((hm.overlapping() ? 1u : 0u) | (unsigned(hm.tile_mask) << 1) | (unsigned(hm.dij_blocks_per_sm) << 8) | (unsigned(hm.pipeline) << 16))));
+          uintptr_t((hm.overlapping() ? 1u : 0u) | (unsigned(hm.tile_mask) << 1))));
       uint64_t cfl_bits;
       std::memcpy(&cfl_bits, &hm.cfl, sizeof(cfl_bits));
       key.push_back(reinterpret_cast<const void *>(cfl_bits));
@@ -1597,15 +1550,6 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
     }
     if (const char *env = std::getenv("RYUJIN_B200_OVERLAP"))
       hm->overlap = std::string(env) != "0";
-    if (const char *env = std::getenv("RYUJIN_B200_STEP2_CONCURRENT"))
-      hm->dij_blocks_per_sm = std::atoi(env);
-    if (const char *env = std::getenv("RYUJIN_B200_PIPELINE"))
-      hm->pipeline = std::atoi(env);
-    if (hm->dij_blocks_per_sm > 0 || hm->pipeline) {
-      RJ_CUDA(cudaStreamCreateWithFlags(&hm->aux_stream, cudaStreamNonBlocking));
-      RJ_CUDA(cudaEventCreateWithFlags(&hm->ev_aux_fork, cudaEventDisableTiming));
-      RJ_CUDA(cudaEventCreateWithFlags(&hm->ev_aux_join, cudaEventDisableTiming));
-    }
 
     /* InitialValues::parse_parameters_callback: normalize direction */
     InitialValuesDevice &d = hm->iv;
