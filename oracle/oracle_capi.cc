@@ -5,6 +5,7 @@
 // restatements in orc_*.h.
 
 #include "orc_euler.h"
+#include "orc_euler_aeos.h"
 #include "orc_integrator.h"
 #include "orc_mesh.h"
 #include "orc_mesh_quads.h"
@@ -51,6 +52,29 @@ namespace
     bool has_mesh = false;
     OfflineData<dim> od;
   };
+
+  /* layout: oracle/orc.py AEOS_PARAM_FIELDS */
+  euler_aeos::Parameters make_aeos_params(const double *p)
+  {
+    euler_aeos::Parameters prm;
+    prm.eos = euler_aeos::Eos(int(p[0]));
+    prm.gamma = p[1];
+    prm.covolume_b = p[2];
+    prm.reference_pressure = p[3];
+    prm.reference_specific_internal_energy = p[4];
+    prm.vdw_a = p[5];
+    prm.compute_strict_bounds = p[6] != 0.;
+    prm.reference_density = p[7];
+    prm.vacuum_state_relaxation_small = p[8];
+    prm.vacuum_state_relaxation_large = p[9];
+    prm.indicator_evc_factor = p[10];
+    prm.limiter_iterations = (unsigned int)p[11];
+    prm.limiter_newton_tolerance = p[12];
+    prm.limiter_newton_max_iterations = (unsigned int)p[13];
+    prm.limiter_relaxation_factor = p[14];
+    prm.expensive_bounds_check = p[15] != 0.;
+    return prm;
+  }
 
   euler::Parameters make_params(const double *p)
   {
@@ -123,23 +147,33 @@ namespace
   };
 
   template <int dim>
-  struct EulerSim : SimBase {
+  struct EulerTraits {
     using Sys = euler::System<dim>;
-    using Desc = Description<Sys,
-                             euler::RiemannSolver<dim>,
-                             euler::Indicator<dim>,
-                             euler::Limiter<dim>>;
+    using Prm = euler::Parameters;
+    using Desc = Description<Sys, euler::RiemannSolver<dim>, euler::Indicator<dim>, euler::Limiter<dim>>;
+  };
+  template <int dim>
+  struct AeosTraits {
+    using Sys = euler_aeos::System<dim>;
+    using Prm = euler_aeos::Parameters;
+    using Desc = Description<Sys, euler_aeos::RiemannSolver<dim>, euler_aeos::Indicator<dim>, euler_aeos::Limiter<dim>>;
+  };
+
+  template <int dim, class Traits>
+  struct GasSim : SimBase {
+    using Sys = typename Traits::Sys;
+    using Desc = typename Traits::Desc;
     using Module = HyperbolicModule<Desc, dim>;
     using SV = typename Module::StateVector;
 
     OfflineHolder<dim> *off;
     Sys sys;
-    euler::InitialValues<dim> iv;
+    euler::InitialValues<dim, Sys> iv;
     std::unique_ptr<Module> module;
     std::unique_ptr<TimeIntegrator<Desc, dim>> ti;
     std::vector<SV> slots; /* slot 0 = the state vector of the time loop */
 
-    EulerSim(OfflineHolder<dim> *o, const euler::Parameters &prm)
+    GasSim(OfflineHolder<dim> *o, const typename Traits::Prm &prm)
         : off(o)
         , sys(prm)
         , iv(sys)
@@ -286,6 +320,11 @@ namespace
       out3[2] = l2;
     }
   };
+  template <int dim>
+  using EulerSim = GasSim<dim, EulerTraits<dim>>;
+  template <int dim>
+  using AeosSim = GasSim<dim, AeosTraits<dim>>;
+
   template <int dim>
   struct SwSim : SimBase {
     using Sys = sw::System<dim>;
@@ -1044,6 +1083,113 @@ void *orc_sim_create_euler(void *offline, const double *params, const double *iv
     });
   });
   return rc == 0 ? result : nullptr;
+}
+
+/* euler aeos: params = AEOS_PARAM_FIELDS, iv as for orc_sim_create_euler */
+void *orc_sim_create_aeos(void *offline, const double *params, const double *iv)
+{
+  void *result = nullptr;
+  const int rc = guarded([&] {
+    WITH_OFFLINE(offline, {
+      auto *sim = new AeosSim<D>(&H, make_aeos_params(params));
+      sim->iv.kind = euler::InitialStateKind(int(iv[0]));
+      for (int c = 0; c < D; ++c) {
+        sim->iv.transform.direction[c] = iv[1 + c];
+        sim->iv.transform.position[c] = iv[4 + c];
+      }
+      for (int c = 0; c < 3; ++c) {
+        sim->iv.primitive[c] = iv[7 + c];
+        sim->iv.primitive_left[c] = iv[7 + c];
+        sim->iv.primitive_right[c] = iv[10 + c];
+      }
+      sim->iv.mach_number = iv[13];
+      sim->iv.beta = iv[14];
+      sim->finalize();
+      result = static_cast<SimBase *>(sim);
+    });
+  });
+  return rc == 0 ? result : nullptr;
+}
+
+/* tests/euler_aeos/riemann_solver{,-strict}.cc: 1D primitive states (rho, u, p, gamma);
+ * out = (lambda_max, p_2, p_star_RS, p_star_SS, p_star_interpolated, p_star_failsafe, a_i, a_j) */
+int orc_aeos_riemann(const double *params, const double *state_i, const double *state_j, double *out)
+{
+  return guarded([&] {
+    euler_aeos::System<1> sys(make_aeos_params(params));
+    euler_aeos::RiemannSolver<1> rs(sys);
+    auto rd = [&](const double *s) {
+      const double x = 1. - sys.b * s[0];
+      std::array<double, 5> r{{s[0], s[1], s[2], s[3], std::sqrt(s[3] * s[2] / (s[0] * x))}};
+      return r;
+    };
+    const auto ri = rd(state_i), rj = rd(state_j);
+    double p_2 = 0.;
+    out[0] = rs.compute(ri, rj, &p_2);
+    out[1] = p_2;
+    out[2] = rs.p_star_RS_full(ri, rj);
+    out[3] = rs.p_star_SS_full(ri, rj);
+    out[4] = rs.p_star_interpolated(ri, rj);
+    out[5] = rs.p_star_failsafe(ri, rj);
+    out[6] = ri[4];
+    out[7] = rj[4];
+  });
+}
+
+/* tests/euler_aeos/limiter{,-NASG}.cc (dim = 1): out = (l, success, surrogate specific entropy(U, gamma)) */
+int orc_aeos_limiter(const double *params, const double *U, const double *P, const double *bounds, double *out)
+{
+  return guarded([&] {
+    euler_aeos::System<1> sys(make_aeos_params(params));
+    euler_aeos::Limiter<1> lim(sys);
+    euler_aeos::System<1>::state_type u{{U[0], U[1], U[2]}}, pp{{P[0], P[1], P[2]}};
+    euler_aeos::System<1>::bounds_type b{{bounds[0], bounds[1], bounds[2], bounds[3]}};
+    bool success = true;
+    out[0] = lim.limit(b, u, pp, success);
+    out[1] = success ? 1. : 0.;
+    out[2] = sys.surrogate_specific_entropy(u, bounds[3]);
+  });
+}
+
+/* tests/euler_aeos/hyperbolic_system.cc: U (dim + 2), gamma -> internal energy, its derivative (k),
+ * surrogate specific entropy, harten entropy, its derivative (k), surrogate pressure, surrogate
+ * gamma, f (k * dim) */
+int orc_aeos_system_quantities(int dim, const double *params, const double *U, double gamma, double *out)
+{
+  return guarded([&] {
+    auto run = [&](auto dimc) {
+      constexpr int d = decltype(dimc)::value;
+      constexpr int k = d + 2;
+      euler_aeos::System<d> sys(make_aeos_params(params));
+      typename euler_aeos::System<d>::state_type u;
+      for (int c = 0; c < k; ++c)
+        u[c] = U[c];
+      int o = 0;
+      out[o++] = sys.internal_energy(u);
+      const auto ied = sys.internal_energy_derivative(u);
+      for (int c = 0; c < k; ++c)
+        out[o++] = ied[c];
+      out[o++] = sys.surrogate_specific_entropy(u, gamma);
+      const double eta = sys.surrogate_harten_entropy(u, gamma);
+      out[o++] = eta;
+      const auto hd = sys.surrogate_harten_entropy_derivative(u, eta, gamma);
+      for (int c = 0; c < k; ++c)
+        out[o++] = hd[c];
+      const double p = sys.surrogate_pressure(u, gamma);
+      out[o++] = p;
+      out[o++] = sys.surrogate_gamma(u, p);
+      const auto f = sys.f(u, p);
+      for (int c = 0; c < k; ++c)
+        for (int e = 0; e < d; ++e)
+          out[o++] = f[c][e];
+    };
+    if (dim == 1)
+      run(std::integral_constant<int, 1>());
+    else if (dim == 2)
+      run(std::integral_constant<int, 2>());
+    else
+      run(std::integral_constant<int, 3>());
+  });
 }
 
 /* iv = (kind, direction[3], position[3], p[4]) */

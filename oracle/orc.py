@@ -44,6 +44,20 @@ EULER_PARAM_DEFAULTS = dict(
     expensive_bounds_check=0,
 )
 
+AEOS_POLYTROPIC_GAS, AEOS_NOBLE_ABEL_STIFFENED_GAS, AEOS_VAN_DER_WAALS = 0, 1, 2
+AEOS_PARAM_FIELDS = (
+    "eos", "gamma", "covolume_b", "reference_pressure", "reference_specific_internal_energy", "vdw_a",
+    "compute_strict_bounds", "reference_density", "vacuum_state_relaxation_small", "vacuum_state_relaxation_large",
+    "indicator_evc_factor", "limiter_iterations", "limiter_newton_tolerance", "limiter_newton_max_iterations",
+    "limiter_relaxation_factor", "expensive_bounds_check",
+)
+AEOS_PARAM_DEFAULTS = dict(
+    eos=AEOS_POLYTROPIC_GAS, gamma=7.0 / 5.0, covolume_b=0.0, reference_pressure=0.0, reference_specific_internal_energy=0.0,
+    vdw_a=0.0, compute_strict_bounds=1, reference_density=1.0, vacuum_state_relaxation_small=1.0e2,
+    vacuum_state_relaxation_large=1.0e4, indicator_evc_factor=1.0, limiter_iterations=2, limiter_newton_tolerance=1.0e-10,
+    limiter_newton_max_iterations=2, limiter_relaxation_factor=1.0, expensive_bounds_check=0,
+)
+
 SW_PARAM_FIELDS = (
     "gravity",
     "manning_friction_coefficient",
@@ -108,6 +122,15 @@ def euler_params(**kw):
     return np.array([float(p[f]) for f in EULER_PARAM_FIELDS], dtype=np.float64)
 
 
+def aeos_params(**kw):
+    p = dict(AEOS_PARAM_DEFAULTS)
+    for k, v in kw.items():
+        if k not in p:
+            raise KeyError(k)
+        p[k] = v
+    return np.array([float(p[f]) for f in AEOS_PARAM_FIELDS], dtype=np.float64)
+
+
 def sw_params(**kw):
     p = dict(SW_PARAM_DEFAULTS)
     for k, v in kw.items():
@@ -169,6 +192,7 @@ class Oracle:
         L.orc_offline_from_arrays.restype = C.c_void_p
         L.orc_sim_create_euler.restype = C.c_void_p
         L.orc_sim_create_sw.restype = C.c_void_p
+        L.orc_sim_create_aeos.restype = C.c_void_p
         L.orc_sim_last_tau_max.restype = C.c_double
         L.orc_sim_last_tau_max.argtypes = [C.c_void_p]
         self.kind = "reference-pow(VCL)" if L.orc_uses_vcl() else "port"
@@ -209,6 +233,34 @@ class Oracle:
         n = np.ascontiguousarray(n_ij, dtype=np.float64)
         self._check(self.lib.orc_euler_riemann_states(int(dim), _dp(euler_params(**prm)), _dp(a), _dp(b), _dp(n), C.byref(lam)))
         return lam.value
+
+    # -- euler aeos unit level --------------------------------------------------
+    def aeos_riemann(self, state_i, state_j, **prm):
+        """tests/euler_aeos/riemann_solver*.cc: 1D primitive states (rho, u, p, gamma)"""
+        out = np.zeros(8)
+        si, sj = np.asarray(state_i, dtype=np.float64), np.asarray(state_j, dtype=np.float64)
+        self._check(self.lib.orc_aeos_riemann(_dp(aeos_params(**prm)), _dp(si), _dp(sj), _dp(out)))
+        keys = ("lambda_max", "p_2", "p_star_RS", "p_star_SS", "p_star_interpolated", "p_star_failsafe", "a_left", "a_right")
+        return dict(zip(keys, out.tolist()))
+
+    def aeos_limiter(self, U, P, bounds, **prm):
+        out = np.zeros(3)
+        u, p, b = (np.ascontiguousarray(x, dtype=np.float64) for x in (U, P, bounds))
+        self._check(self.lib.orc_aeos_limiter(_dp(aeos_params(**prm)), _dp(u), _dp(p), _dp(b), _dp(out)))
+        return dict(l=out[0], success=bool(out[1]), specific_entropy=out[2])
+
+    def aeos_system_quantities(self, dim, U, gamma, **prm):
+        k = dim + 2
+        out = np.zeros(1 + k + 2 + k + 2 + k * dim)
+        u = np.ascontiguousarray(U, dtype=np.float64)
+        self._check(self.lib.orc_aeos_system_quantities(int(dim), _dp(aeos_params(**prm)), _dp(u), C.c_double(gamma), _dp(out)))
+        o = 0
+        res = {}
+        for name, n in (("internal_energy", 1), ("internal_energy_derivative", k), ("specific_entropy", 1), ("harten_entropy", 1),
+                        ("harten_entropy_derivative", k), ("surrogate_pressure", 1), ("surrogate_gamma", 1), ("f", k * dim)):
+            res[name] = out[o] if n == 1 else out[o:o + n].copy()
+            o += n
+        return res
 
     def sw_riemann(self, state_i, state_j, **prm):
         """tests/shallow_water/riemann_solver.cc: conserved 1D states (h, m)"""
@@ -402,6 +454,26 @@ class Offline:
         if not handle:
             raise OracleError(self.o.lib.orc_last_error().decode())
         return Sim(self, handle)
+
+
+def _aeos_sim(offline, kind=UNIFORM, direction=(1.0, 0.0, 0.0), position=(1.0, 0.0, 0.0), primitive=(1.4, 3.0, 1.0),
+              primitive_right=(1.4, 0.0, 1.0), mach=2.0, beta=5.0, **prm):
+    """euler aeos simulation on this offline data (orc_euler_aeos.h)"""
+    iv = np.zeros(15)
+    iv[0] = kind
+    iv[1:4] = list(direction) + [0.0] * (3 - len(direction))
+    iv[4:7] = list(position) + [0.0] * (3 - len(position))
+    iv[7:10] = primitive
+    iv[10:13] = primitive_right
+    iv[13] = mach
+    iv[14] = beta
+    handle = offline.o.lib.orc_sim_create_aeos(offline.h, _dp(aeos_params(**prm)), _dp(iv))
+    if not handle:
+        raise OracleError(offline.o.lib.orc_last_error().decode())
+    return Sim(offline, handle)
+
+
+Offline.aeos_sim = _aeos_sim
 
 
 def _sw_sim(offline, kind=SW_UNIFORM, direction=(1.0, 0.0, 0.0), position=(1.0, 0.0, 0.0), p=(1.0, 1.0, 0.0, 0.0), **prm):

@@ -42,6 +42,7 @@ namespace orc
       static constexpr int n_bounds = 3;          /* rho_min, rho_max, s_min */
       static constexpr int n_initial_precomputed = 0;
       static constexpr bool shallow_water = false;
+      static constexpr bool aeos = false;
       static constexpr bool have_source_terms = false;
       static constexpr bool have_high_order_flux = false;
       using state_type = std::array<double, k>;

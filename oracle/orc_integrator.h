@@ -310,9 +310,11 @@ namespace orc
      * verification decks of the reference) */
     enum class InitialStateKind { uniform = 0, contrast = 1, isentropic_vortex = 2, leblanc = 3, rarefaction = 4 };
 
-    template <int dim>
+    /* SysT: euler::System<dim>, or euler_aeos::System<dim> (the reference shares the
+     * EulerInitialStateLibrary between the two equations; only from_initial_state differs) */
+    template <int dim, class SysT = System<dim>>
     struct InitialValues {
-      using Sys = System<dim>;
+      using Sys = SysT;
       using state_type = typename Sys::state_type;
 
       const Sys &sys;

@@ -219,14 +219,51 @@ namespace orc
       }
 
       const unsigned int n = od_.n_owned;
+      if constexpr (System::aeos) {
+        /* two precomputation cycles (euler_aeos/hyperbolic_system.h:433,843-975): cycle 0 per
+         * node, [ghost exchange of the precomputed vector], cycle 1 with a loop over the stencil */
 #pragma omp parallel for schedule(static)
-      for (unsigned int i = 0; i < n; ++i) {
-        if (od_.row_length(i) == 1)
-          continue;
-        const auto U_i = get(sv.U, i);
-        const auto prec_i = sys_.precompute(U_i);
-        for (int c = 0; c < n_prec; ++c)
-          sv.prec[std::size_t(i) * n_prec + c] = prec_i[c];
+        for (unsigned int i = 0; i < n; ++i) {
+          if (od_.row_length(i) == 1)
+            continue;
+          const auto prec_i = sys_.precompute_cycle_0(get(sv.U, i));
+          for (int c = 0; c < n_prec; ++c)
+            sv.prec[std::size_t(i) * n_prec + c] = prec_i[c];
+        }
+        std::vector<double> gamma_min(n, 0.);
+#pragma omp parallel for schedule(static)
+        for (unsigned int i = 0; i < n; ++i) {
+          const unsigned int row_length = od_.row_length(i);
+          if (row_length == 1)
+            continue;
+          double g = sv.prec[std::size_t(i) * n_prec + 1];
+          for (unsigned int col_idx = 1; col_idx < row_length; ++col_idx) {
+            const unsigned int j = od_.cols[od_.row_ptr[i] + col_idx];
+            const double gamma_j = sys_.surrogate_gamma(get(sv.U, j), sv.prec[std::size_t(j) * n_prec + 0]);
+            g = std::min(g, gamma_j);
+          }
+          gamma_min[i] = g;
+        }
+#pragma omp parallel for schedule(static)
+        for (unsigned int i = 0; i < n; ++i) {
+          if (od_.row_length(i) == 1)
+            continue;
+          auto prec_i = getp(sv.prec, i);
+          prec_i[1] = gamma_min[i];
+          sys_.precompute_cycle_1_finish(prec_i, get(sv.U, i));
+          for (int c = 0; c < n_prec; ++c)
+            sv.prec[std::size_t(i) * n_prec + c] = prec_i[c];
+        }
+      } else {
+#pragma omp parallel for schedule(static)
+        for (unsigned int i = 0; i < n; ++i) {
+          if (od_.row_length(i) == 1)
+            continue;
+          const auto U_i = get(sv.U, i);
+          const auto prec_i = sys_.precompute(U_i);
+          for (int c = 0; c < n_prec; ++c)
+            sv.prec[std::size_t(i) * n_prec + c] = prec_i[c];
+        }
       }
     }
 
@@ -286,7 +323,11 @@ namespace orc
             Vec<dim> n_ij;
             for (int d = 0; d < dim; ++d)
               n_ij[d] = c_ij[d] * nrm_inverse;
-            const double lambda_max = riemann_solver.compute(U_i, U_j, n_ij);
+            double lambda_max;
+            if constexpr (System::aeos)
+              lambda_max = riemann_solver.compute(U_i, getp(old_prec, i), U_j, getp(old_prec, j), n_ij);
+            else
+              lambda_max = riemann_solver.compute(U_i, U_j, n_ij);
             dij_[e] = nrm * lambda_max;
           }
 
@@ -313,7 +354,11 @@ namespace orc
           for (int d = 0; d < dim; ++d)
             n_ji[d] = c_ji[d] * norm_ji_inverse;
           const double d_ij = dij_[e];
-          const double lambda_max = riemann_solver.compute(U_j, U_i, n_ji);
+          double lambda_max;
+          if constexpr (System::aeos)
+            lambda_max = riemann_solver.compute(U_j, getp(old_prec, j), U_i, getp(old_prec, i), n_ji);
+          else
+            lambda_max = riemann_solver.compute(U_j, U_i, n_ji);
           const double d_ji = norm_ji * lambda_max;
           dij_[e] = std::max(d_ij, d_ji);
         }
@@ -408,7 +453,10 @@ namespace orc
               }
             }
 
-            limiter.reset(U_i);
+            if constexpr (System::aeos)
+              limiter.reset(getp(old_prec, i), U_i, flux_i);
+            else
+              limiter.reset(U_i);
 
             state_type affine_shift;
             affine_shift.fill(0.);
@@ -484,7 +532,10 @@ namespace orc
                   F_iH[c] += d_ijH * diff;
                   P_ij[c] += (d_ijH - d_ij) * diff;
                 }
-                limiter.accumulate(getp(old_prec, j), U_j, scaled_c_ij);
+                if constexpr (System::aeos)
+                  limiter.accumulate(getp(old_prec, j), U_j, flux_j, scaled_c_ij);
+                else
+                  limiter.accumulate(getp(old_prec, j), U_j, scaled_c_ij);
               }
 
               if constexpr (System::have_source_terms) {

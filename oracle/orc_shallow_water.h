@@ -42,6 +42,7 @@ namespace orc
       static constexpr int n_initial_precomputed = 1; /* bathymetry */
       static constexpr int n_bounds = 5;              /* h_min, h_max, h_small, kin_max, v2_max */
       static constexpr bool shallow_water = true;
+      static constexpr bool aeos = false;
       static constexpr bool have_source_terms = true;
       static constexpr bool have_high_order_flux = true;
       using state_type = std::array<double, k>;

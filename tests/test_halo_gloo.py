@@ -32,13 +32,13 @@ def _f_mat(gi, gj):
     return gi.astype(np.float64) * 1.0e4 + gj.astype(np.float64) + 0.5
 
 
-def _worker(rank, world, port, n_cells, q):
+def _worker(rank, world, port, n_cells, q, partition=None):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
         dist.init_process_group("gloo", rank=rank, world_size=world)
         dim = len(n_cells)
-        mesh = rj.CartesianMesh(n_cells, [0.0] * dim, [1.0] * dim, [B.dirichlet] * (2 * dim))
+        mesh = rj.CartesianMesh(n_cells, [0.0] * dim, [1.0] * dim, [B.dirichlet] * (2 * dim), partition=partition)
         host = rj.HostOfflineData(mesh, rank, world)
         od = rj.OfflineData(host, host_layout_only=True)
         neighbors, send_rows, mat_send = od.exchange_lists()
@@ -104,12 +104,15 @@ def _worker(rank, world, port, n_cells, q):
         q.put((rank, "error: %s\n%s" % (exc, traceback.format_exc())))
 
 
-@pytest.mark.parametrize("n_cells,world", [([6, 9], 2), ([4, 3, 7], 2), ([5, 11], 3)])
-def test_exchange_lists_over_gloo(n_cells, world):
+@pytest.mark.parametrize("n_cells,world,partition", [([6, 9], 2, None), ([4, 3, 7], 2, None), ([5, 11], 3, None),
+                                                     ([7, 9], 4, [2, 2]), ([5, 6, 7], 4, [1, 2, 2])])
+def test_exchange_lists_over_gloo(n_cells, world, partition):
+    """slabs and block partitions (face, edge and corner neighbours): one buffer [component][row] per
+    neighbour and exchange, as the NCCL path sends it"""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_cells, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_cells, q, partition)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=180) for _ in procs]
