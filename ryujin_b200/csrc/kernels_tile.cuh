@@ -24,6 +24,9 @@ unsigned char *rj_emu_dynamic_smem(); /* tests/host_emulation/host_emulation.cc 
 #ifndef RJ_TILE_DEFAULT_MASK
 #define RJ_TILE_DEFAULT_MASK 3 /* bit 0: step 5 tiled, bit 1: step 6 tiled */
 #endif
+#ifndef RJ_OVERLAP_MODE_DEFAULT
+#define RJ_OVERLAP_MODE_DEFAULT 1
+#endif
 #ifndef RJ_TILE_W
 #define RJ_TILE_W 4 /* warps per slice */
 #endif

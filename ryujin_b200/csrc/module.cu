@@ -90,6 +90,7 @@ struct rj_hyperbolic_module {
    * "fire the exchange once the export rows are done").  `cur` is the stream launch() and the
    * exchanges currently target. */
   cudaStream_t comm_stream = nullptr;
+  int overlap_mode = RJ_OVERLAP_MODE_DEFAULT; /* 1: export rows, then exchange || interior rows; 2: (export rows, exchange) || interior rows */
   cudaStream_t cur = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap = true;
@@ -717,8 +718,19 @@ namespace rjb
       /* sweep(f): f(begin, end) on the export rows, `exchange` on the communication stream,
        * f on the interior rows meanwhile; the main stream continues after both */
       auto sweep = [&](auto &&f, auto &&exchange) {
-        f(0u, nx);
-        if (ov) {
+        if (ov && overlap_mode == 2) {
+          /* the (small) export-row launch itself goes to the high-priority communication stream
+           * and runs CONCURRENTLY with the interior rows on the main stream: no under-filled launch
+           * in front of the interior sweep (8M DoFs per rank: 80k export rows = half a wave) */
+          fork_comm();
+          f(0u, nx);
+          tag(P_OTHER);
+          exchange();
+          continue_main();
+          f(nx, n_owned);
+          join_comm();
+        } else if (ov) {
+          f(0u, nx);
           fork_comm();
           tag(P_OTHER);
           exchange();
@@ -726,6 +738,7 @@ namespace rjb
           f(nx, n_owned);
           join_comm();
         } else {
+          f(0u, nx);
           tag(P_OTHER);
           exchange();
         }
@@ -1105,7 +1118,7 @@ namespace rjb
         key.push_back(s->aux);
       }
       key.push_back(reinterpret_cast<const void *>(
-          uintptr_t((hm.overlapping() ? 1u : 0u) | (unsigned(hm.tile_mask) << 1))));
+          uintptr_t((hm.overlapping() ? unsigned(hm.overlap_mode) : 0u) | (unsigned(hm.tile_mask) << 2))));
       uint64_t cfl_bits;
       std::memcpy(&cfl_bits, &hm.cfl, sizeof(cfl_bits));
       key.push_back(reinterpret_cast<const void *>(cfl_bits));
@@ -1548,8 +1561,11 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
       RJ_CUDA(cudaEventCreateWithFlags(&hm->ev_fork, cudaEventDisableTiming));
       RJ_CUDA(cudaEventCreateWithFlags(&hm->ev_join, cudaEventDisableTiming));
     }
-    if (const char *env = std::getenv("RYUJIN_B200_OVERLAP"))
+    if (const char *env = std::getenv("RYUJIN_B200_OVERLAP")) {
       hm->overlap = std::string(env) != "0";
+      if (hm->overlap)
+        hm->overlap_mode = std::atoi(env) == 2 ? 2 : 1;
+    }
 
     /* InitialValues::parse_parameters_callback: normalize direction */
     InitialValuesDevice &d = hm->iv;

@@ -134,7 +134,7 @@ def main():
             ("sw_dam2d", [18, 17], 6, dict(partition=p2), 1e-7),
         ]
     for case, n_cells, cycles, kw, tol in cases:
-        os.environ["RYUJIN_B200_OVERLAP"] = "1"
+        os.environ["RYUJIN_B200_OVERLAP"] = os.environ.get("RJ_TEST_OVERLAP_MODE", "1")
         U, taus, counters = run(case, n_cells, cycles, world, **kw)
         os.environ["RYUJIN_B200_OVERLAP"] = "0"
         U_serial, taus_serial, counters_serial = run(case, n_cells, cycles, world, **kw)
