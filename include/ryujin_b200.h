@@ -53,7 +53,16 @@ enum rj_boundary_id {
 };
 
 /* Equation modules ("Description"), source/<equation>/description.h */
-enum rj_equation { RJ_EQUATION_EULER = 0, RJ_EQUATION_SHALLOW_WATER = 1 };
+enum rj_equation { RJ_EQUATION_EULER = 0, RJ_EQUATION_SHALLOW_WATER = 1, RJ_EQUATION_EULER_AEOS = 2 };
+
+/* EquationOfStateLibrary of the euler_aeos module: the analytic equations of state of
+ * source/euler_aeos/equation_of_state_{polytropic_gas,noble_abel_stiffened_gas,van_der_waals}.h
+ * (the tabulated "sesame" and the Jones-Wilkins-Lee equations of state are not offered) */
+enum rj_equation_of_state {
+  RJ_EOS_POLYTROPIC_GAS = 0,
+  RJ_EOS_NOBLE_ABEL_STIFFENED_GAS = 1,
+  RJ_EOS_VAN_DER_WAALS = 2
+};
 
 /* IDViolationStrategy, source/hyperbolic_module.h:37-52 */
 enum rj_id_violation_strategy { RJ_STRATEGY_WARN = 0, RJ_STRATEGY_RAISE_EXCEPTION = 1 };
@@ -278,6 +287,17 @@ typedef struct rj_equation_desc {
   double dry_state_relaxation_factor;
   double dry_state_relaxation_small;
   double dry_state_relaxation_large;
+  /* euler_aeos/hyperbolic_system.h:456-490 and the parameters of the selected equation of state:
+   * gamma (above) is its "gamma"; covolume b (noble abel stiffened gas, van der waals), reference
+   * pressure and reference specific internal energy (noble abel stiffened gas), vdw a.  The
+   * interpolatory covolume / pinfty / q of the surrogate follow from them as in the
+   * parse_parameters_call_back of each equation of state. */
+  int32_t equation_of_state; /* rj_equation_of_state */
+  int32_t compute_strict_bounds;
+  double covolume_b;
+  double reference_pressure;
+  double reference_specific_internal_energy;
+  double vdw_a;
 } rj_equation_desc;
 
 typedef struct rj_module_params {

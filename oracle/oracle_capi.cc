@@ -120,6 +120,7 @@ namespace
     virtual ~SimBase() = default;
     virtual int k() const = 0;
     virtual int n_bounds() const = 0;
+    virtual int n_precomputed() const = 0;
     virtual unsigned int n() const = 0;
     virtual std::size_t nnz() const = 0;
     virtual void interpolate(double t, int slot) = 0;
@@ -196,6 +197,7 @@ namespace
 
     int k() const override { return Sys::k; }
     int n_bounds() const override { return Sys::n_bounds; }
+    int n_precomputed() const override { return Sys::n_precomputed; }
     unsigned int n() const override { return off->od.n_owned; }
     std::size_t nnz() const override { return off->od.cols.size(); }
 
@@ -373,6 +375,7 @@ namespace
 
     int k() const override { return Sys::k; }
     int n_bounds() const override { return Sys::n_bounds; }
+    int n_precomputed() const override { return Sys::n_precomputed; }
     unsigned int n() const override { return off->od.n_owned; }
     std::size_t nnz() const override { return off->od.cols.size(); }
 
@@ -1214,6 +1217,7 @@ void *orc_sim_create_sw(void *offline, const double *params, const double *iv)
 }
 
 int orc_sim_n_bounds(void *s) { return static_cast<SimBase *>(s)->n_bounds(); }
+int orc_sim_n_precomputed(void *s) { return static_cast<SimBase *>(s)->n_precomputed(); }
 
 int orc_sim_set_initial_precomputed(void *s, const double *values)
 {

@@ -513,6 +513,7 @@ class Sim:
         self.h = C.c_void_p(handle)
         self.k = int(self.o.lib.orc_sim_k(self.h))
         self.n_bounds = int(self.o.lib.orc_sim_n_bounds(self.h))
+        self.n_precomputed = int(self.o.lib.orc_sim_n_precomputed(self.h))
         self.n = offline.n
         self.nnz = offline.nnz
 
@@ -536,7 +537,7 @@ class Sim:
         return u
 
     def get_prec(self, slot=0):
-        p = np.zeros((self.n, 2))
+        p = np.zeros((self.n, self.n_precomputed))
         self.o._check(self.o.lib.orc_sim_get_prec(self.h, int(slot), _dp(p)))
         return p
 

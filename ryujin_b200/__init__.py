@@ -9,6 +9,7 @@ from .hyperbolic_module import (  # noqa: F401
     CFLRecoveryStrategy,
     Communicator,
     Equation,
+    EquationOfState,
     HyperbolicModule,
     HyperbolicSystem,
     IDViolationStrategy,

@@ -120,6 +120,12 @@ class EquationDesc(C.Structure):
         ("dry_state_relaxation_factor", C.c_double),
         ("dry_state_relaxation_small", C.c_double),
         ("dry_state_relaxation_large", C.c_double),
+        ("equation_of_state", C.c_int32),
+        ("compute_strict_bounds", C.c_int32),
+        ("covolume_b", C.c_double),
+        ("reference_pressure", C.c_double),
+        ("reference_specific_internal_energy", C.c_double),
+        ("vdw_a", C.c_double),
     ]
 
 

@@ -284,6 +284,7 @@ namespace rjb
           od->bnormal = upload(nrm);
           od->bposition = upload(pos);
           od->bid = upload(ids);
+          od->h_boundary_ids = ids;
         }
       }
 

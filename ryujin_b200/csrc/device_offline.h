@@ -69,6 +69,7 @@ struct rj_offline {
   /* host mirrors for introspection / CSR <-> sliced index maps */
   std::vector<uint32_t> h_slice_offsets;
   std::vector<uint32_t> h_row_length;
+  std::vector<int32_t> h_boundary_ids; /* host copy: equations reject ids they do not implement */
   std::vector<uint32_t> h_cols, h_transposed; /* host-only layouts */
   std::vector<uint32_t> h_send_rows, h_mat_send_entries;
   bool host_only = false;

@@ -36,6 +36,7 @@ namespace rjb
     static constexpr int n_prec = 2;       /* (specific entropy, Harten entropy) */
     static constexpr int n_bounds = 3;     /* rho_min, rho_max, s_min */
     static constexpr bool shallow_water = false;
+    static constexpr bool aeos = false;
     static constexpr bool have_source_terms = false;
     static constexpr bool have_high_order_flux = false;
     using Params = EulerParams;

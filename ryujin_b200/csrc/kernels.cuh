@@ -294,6 +294,43 @@ namespace rjb
   }
 
 
+  /* Second precomputation cycle of equations that have one (euler_aeos/hyperbolic_system.h:
+   * 943-973): gamma_min_i = min over the stencil of the surrogate gamma of (U_j, p_j), then the
+   * surrogate entropies of row i.  Owned rows only (a ghost row's stencil is not local): the
+   * precomputed vector is exchanged afterwards, as the reference does between its cycles.  Reads
+   * component 0 of other rows, writes components 1.. of its own row: no hazard within the launch. */
+  template <class Eq>
+  __global__ void __launch_bounds__(128) k_precompute_stencil(StencilView v,
+                                                              typename Eq::Params prm,
+                                                              uint32_t row_begin,
+                                                              uint32_t row_end,
+                                                              const double *__restrict__ U,
+                                                              double *prec)
+  {
+    constexpr int k = Eq::k, np = Eq::n_prec;
+    RowInfo r;
+    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+      return;
+    const uint32_t i = r.i;
+    double U_i[k], prec_i[np];
+    load_state<k>(U, v.ld, i, U_i);
+    load_state<np>(prec, v.ld, i, prec_i);
+    double gamma_min = prec_i[1];
+    for (uint32_t col = 1; col < r.len; ++col) {
+      const uint32_t j = v.cols[r.base + col * 32];
+      double U_j[k];
+      load_state<k>(U, v.ld, j, U_j);
+      const double p_j = prec[j];
+      gamma_min = fmin(gamma_min, Eq::surrogate_gamma(prm, U_j, p_j));
+    }
+    prec_i[1] = gamma_min;
+    Eq::precompute_finish(prm, U_i, prec_i);
+#pragma unroll
+    for (int q = 1; q < np; ++q)
+      prec[size_t(q) * v.ld + i] = prec_i[q];
+  }
+
+
   /* ---------------------------------------------------------------------- *
    * Step 2: off-diagonal d_ij for j > i and alpha_i,
    * hyperbolic_module.template.h:341-424, as two kernels:
@@ -648,7 +685,10 @@ namespace rjb
     }
 
     typename Eq::LimiterAccumulator limiter;
-    limiter.reset();
+    if constexpr (Eq::aeos)
+      limiter.reset(prec_i);
+    else
+      limiter.reset();
 
     const double tau_m_i_inv = tau * m_i_inv;
 
@@ -738,7 +778,10 @@ namespace rjb
           F_iH[q] += d_ijH * diff;
           P_ij[q] += (d_ijH - d_ij) * diff;
         }
-        limiter.accumulate(prm, U_i, U_j, prec_j, scaled_c_ij);
+        if constexpr (Eq::aeos)
+          limiter.accumulate(prm, U_i, flux_i, U_j, flux_j, prec_j, scaled_c_ij);
+        else
+          limiter.accumulate(prm, U_i, U_j, prec_j, scaled_c_ij);
       }
 
       double m_ij = 0.;

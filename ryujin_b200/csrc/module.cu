@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "kernels_tile.cuh"
 #include "shallow_water.cuh"
+#include "euler_aeos.cuh"
 
 #include <nccl.h>
 
@@ -566,6 +567,53 @@ namespace rjb
   }
 
 
+  /* the constructor and parse_parameters_call_back of the selected equation of state
+   * (equation_of_state_noble_abel_stiffened_gas.h:40-75, equation_of_state_van_der_waals.h:40-80) */
+  inline EulerAeosParams make_aeos_params(const rj_equation_desc &eq, const rj_module_params &mp)
+  {
+    EulerAeosParams p;
+    p.eos = eq.equation_of_state;
+    p.gamma = eq.gamma;
+    p.eos_b = p.eos_q = p.eos_pinf = p.vdw_a = 0.;
+    p.b = p.pinf = p.q = 0.;
+    if (eq.equation_of_state == RJ_EOS_NOBLE_ABEL_STIFFENED_GAS) {
+      p.eos_b = p.b = eq.covolume_b;
+      p.eos_pinf = p.pinf = eq.reference_pressure;
+      p.eos_q = p.q = eq.reference_specific_internal_energy;
+    } else if (eq.equation_of_state == RJ_EOS_VAN_DER_WAALS) {
+      p.eos_b = p.b = eq.covolume_b;
+      p.vdw_a = eq.vdw_a;
+      if (eq.covolume_b > 0.)
+        p.pinf = eq.vdw_a / (eq.covolume_b * eq.covolume_b);
+    } else if (eq.equation_of_state != RJ_EOS_POLYTROPIC_GAS)
+      throw InvalidArgument("rj_hyperbolic_module_create: equation of state not available");
+    p.compute_strict_bounds = eq.compute_strict_bounds;
+    p.reference_density = eq.reference_density;
+    p.vacuum_relaxation_small = eq.vacuum_state_relaxation_small;
+    p.vacuum_relaxation_large = eq.vacuum_state_relaxation_large;
+    p.evc_factor = mp.indicator_evc_factor;
+    p.limiter_newton_tolerance = mp.limiter_newton_tolerance;
+    p.limiter_relaxation_factor = mp.limiter_relaxation_factor;
+    p.limiter_newton_max_iterations = mp.limiter_newton_max_iterations;
+    return p;
+  }
+  template <>
+  EulerAeosParams make_params<EulerAeos<1>>(const rj_equation_desc &eq, const rj_module_params &mp)
+  {
+    return make_aeos_params(eq, mp);
+  }
+  template <>
+  EulerAeosParams make_params<EulerAeos<2>>(const rj_equation_desc &eq, const rj_module_params &mp)
+  {
+    return make_aeos_params(eq, mp);
+  }
+  template <>
+  EulerAeosParams make_params<EulerAeos<3>>(const rj_equation_desc &eq, const rj_module_params &mp)
+  {
+    return make_aeos_params(eq, mp);
+  }
+
+
   template <class Eq>
   struct ModuleImpl : rj_hyperbolic_module {
     typename Eq::Params prm;
@@ -647,6 +695,15 @@ namespace rjb
         tag(P_OTHER);
         exchange_vector(state.U, Eq::k);
         precompute(0, od->n_relevant);
+      }
+      if constexpr (Eq::aeos) {
+        /* second precomputation cycle over the stencil of the owned rows, then the ghost rows of
+         * the precomputed vector from their owners (euler_aeos/hyperbolic_system.h:943-973,
+         * hyperbolic_module.template.h:157-160) */
+        tag(P_PRECOMPUTE);
+        launch_rows(k_precompute_stencil<Eq>, 0, od->n_owned, v, prm, 0u, od->n_owned, state.U, state.prec);
+        tag(P_OTHER);
+        exchange_vector(state.prec, Eq::n_prec);
       }
     }
 
@@ -1436,6 +1493,8 @@ void rj_equation_desc_default(rj_equation_desc *eq, int equation)
   eq->dry_state_relaxation_factor = 2.e-1; /* shallow_water/hyperbolic_system.h:659 */
   eq->dry_state_relaxation_small = 1.e2;
   eq->dry_state_relaxation_large = 1.e4;
+  eq->equation_of_state = RJ_EOS_POLYTROPIC_GAS;
+  eq->compute_strict_bounds = 1; /* euler_aeos/hyperbolic_system.h:470-474 */
 }
 
 void rj_module_params_default(rj_module_params *mp)
@@ -1531,6 +1590,17 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
         make(ShallowWater<2>());
       else
         throw InvalidArgument("rj_hyperbolic_module_create: shallow water needs dim 1 or 2");
+    } else if (eq->equation == RJ_EQUATION_EULER_AEOS) {
+      /* dynamic boundaries trap in the reference (euler_aeos/hyperbolic_system.h:1315) */
+      for (int32_t id : od->h_boundary_ids)
+        if (id == RJ_BOUNDARY_DYNAMIC)
+          throw InvalidArgument("rj_hyperbolic_module_create: euler aeos has no dynamic boundary condition");
+      if (od->dim == 1)
+        make(EulerAeos<1>());
+      else if (od->dim == 2)
+        make(EulerAeos<2>());
+      else
+        make(EulerAeos<3>());
     } else
       throw InvalidArgument("rj_hyperbolic_module_create: equation module not available");
 

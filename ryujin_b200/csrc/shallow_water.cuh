@@ -32,6 +32,7 @@ namespace rjb
     static constexpr int n_bounds = 5; /* h_min, h_max, h_small, kin_max, v2_max */
     static constexpr int n_aux = 1;    /* bathymetry Z_i: the per-node part of flux_contribution = (U, Z) */
     static constexpr bool shallow_water = true;
+    static constexpr bool aeos = false;
     static constexpr bool have_source_terms = true;
     static constexpr bool have_high_order_flux = true;
     using Params = ShallowWaterParams;

@@ -15,6 +15,15 @@ from ._lib import Restart, check, lib  # noqa: F401  (Restart re-exported)
 class Equation(enum.IntEnum):
     euler = 0
     shallow_water = 1
+    euler_aeos = 2
+
+
+class EquationOfState(enum.IntEnum):
+    """EquationOfStateLibrary of source/euler_aeos (analytic equations of state)"""
+
+    polytropic_gas = 0
+    noble_abel_stiffened_gas = 1
+    van_der_waals = 2
 
 
 class IDViolationStrategy(enum.IntEnum):
@@ -60,7 +69,10 @@ class InitialState(enum.IntEnum):
 
 class HyperbolicSystem:
     """Runtime parameters of the equation module (B - Equation;
-    source/euler/hyperbolic_system.h:668-684, shallow_water/hyperbolic_system.h:643-674)."""
+    source/euler/hyperbolic_system.h:668-684, shallow_water/hyperbolic_system.h:643-674,
+    euler_aeos/hyperbolic_system.h:456-490 plus the parameters of the selected equation of state:
+    equation_of_state, gamma, covolume_b, reference_pressure, reference_specific_internal_energy,
+    vdw_a, compute_strict_bounds)."""
 
     def __init__(self, equation=Equation.euler, **kw):
         self.desc = _lib.EquationDesc()

@@ -16,7 +16,7 @@ import time
 import numpy as np
 
 from . import prm as _prm
-from .hyperbolic_module import (CFLRecoveryStrategy, Equation, HyperbolicModule, HyperbolicSystem, InitialState,
+from .hyperbolic_module import (CFLRecoveryStrategy, Equation, EquationOfState, HyperbolicModule, HyperbolicSystem, InitialState,
                                 InitialValues, ModuleParameters, TimeIntegrator, TimeSteppingScheme)
 from .offline_data import Boundary, CartesianMesh, OfflineData
 
@@ -36,6 +36,7 @@ SCHEMES = {
 COMPONENT_NAMES = {  # View::component_names, euler/hyperbolic_system.h:240-249, shallow_water/...:207-216
     Equation.euler: {1: ["rho", "m", "E"], 2: ["rho", "m_1", "m_2", "E"], 3: ["rho", "m_1", "m_2", "m_3", "E"]},
     Equation.shallow_water: {1: ["h", "m"], 2: ["h", "m_1", "m_2"]},
+    Equation.euler_aeos: {1: ["rho", "m", "E"], 2: ["rho", "m_1", "m_2", "E"], 3: ["rho", "m_1", "m_2", "m_3", "E"]},
 }
 
 
@@ -153,8 +154,33 @@ class TimeLoop:
                 dry_state_relaxation_factor=B.get_float("dry state relaxation factor", 2.0e-1),
                 dry_state_relaxation_small=B.get_float("dry state relaxation small", 1.0e2),
                 dry_state_relaxation_large=B.get_float("dry state relaxation large", 1.0e4))
+        elif eq_name == "euler aeos":
+            # euler_aeos/hyperbolic_system.h:770-812 + the subsection of the selected equation of state
+            # (equation_of_state_{polytropic_gas,noble_abel_stiffened_gas,van_der_waals}.h)
+            self.equation = Equation.euler_aeos
+            eos_name = B.get_str("equation of state", "polytropic gas")
+            eos_kinds = {"polytropic gas": EquationOfState.polytropic_gas,
+                         "noble abel stiffened gas": EquationOfState.noble_abel_stiffened_gas,
+                         "van der waals": EquationOfState.van_der_waals}
+            if eos_name not in eos_kinds:
+                raise NotOnThePath("equation of state »%s« is not available on the device (polytropic gas, "
+                                   "noble abel stiffened gas, van der waals)" % eos_name)
+            S = B.subsection(eos_name)
+            eos = dict(gamma=S.get_float("gamma", 7.0 / 5.0))
+            S.get_float("gas constant R", 287.052874)  # temperature only: not on the path
+            if eos_name == "noble abel stiffened gas":
+                eos.update(covolume_b=S.get_float("covolume b", 0.0), reference_pressure=S.get_float("reference pressure", 0.0),
+                           reference_specific_internal_energy=S.get_float("reference specific internal energy", 0.0))
+            elif eos_name == "van der waals":
+                eos.update(covolume_b=S.get_float("covolume b", 0.0), vdw_a=S.get_float("vdw a", 0.0))
+            system = HyperbolicSystem(
+                Equation.euler_aeos, equation_of_state=int(eos_kinds[eos_name]),
+                compute_strict_bounds=int(B.get_bool("compute strict bounds", True)),
+                reference_density=B.get_float("reference density", 1.0),
+                vacuum_state_relaxation_small=B.get_float("vacuum state relaxation small", 1.0e2),
+                vacuum_state_relaxation_large=B.get_float("vacuum state relaxation large", 1.0e4), **eos)
         else:
-            raise NotOnThePath("equation »%s« has no B200 plug-in (euler, shallow water)" % eq_name)
+            raise NotOnThePath("equation »%s« has no B200 plug-in (euler, euler aeos, shallow water)" % eq_name)
         if self.dim not in COMPONENT_NAMES[self.equation]:
             raise NotOnThePath("%s is not instantiated for dim = %d" % (eq_name, self.dim))
         self.component_names = COMPONENT_NAMES[self.equation][self.dim]
@@ -202,7 +228,7 @@ class TimeLoop:
         if E.get_float("perturbation", 0.0) != 0.0:
             raise NotOnThePath("random perturbations of the initial state are not generated on the device")
         S = E.subsection(configuration)
-        if self.equation == Equation.euler:
+        if self.equation in (Equation.euler, Equation.euler_aeos):
             if configuration == "uniform":
                 iv = InitialValues(InitialState.uniform, direction, position, primitive=S.get_list("primitive state", [1.4, 3.0, 1.0]))
             elif configuration == "contrast":
@@ -243,7 +269,7 @@ class TimeLoop:
         if self.equation == Equation.euler:
             mp.update(riemann_newton_tolerance=rie.get_float("newton tolerance", 1.0e-10),
                       riemann_newton_max_iterations=rie.get_int("newton max iterations", 0))
-        else:
+        elif self.equation == Equation.shallow_water:
             mp.update(limit_on_kinetic_energy=int(lim.get_bool("limit on kinetic energy", False)),
                       limit_on_square_velocity=int(lim.get_bool("limit on square velocity", True)))
 
@@ -327,6 +353,11 @@ class TimeLoop:
             gamma = self.module.hyperbolic_system.desc.gamma
             p = (gamma - 1.0) * (U[:, -1] - 0.5 * U[:, 0] * np.sum(v * v, axis=1))
             return np.column_stack([U[:, 0], v, p])
+        if self.equation == Equation.euler_aeos:
+            # (rho, v, e) as euler_aeos/hyperbolic_system.h:1481-1500
+            rho = U[:, 0]
+            e = (U[:, -1] - 0.5 * rho * np.sum(v * v, axis=1)) / rho
+            return np.column_stack([rho, v, e])
         return np.column_stack([U[:, 0], v])
 
     def space_averaged_primitive_state(self):
@@ -342,6 +373,7 @@ class TimeLoop:
     def print_time_series(self):
         """<basename>-<manifold>-R0000-space_averaged_time_series.dat as the reference writes it"""
         names = {Equation.euler: ["rho"] + ["v_%d" % (d + 1) for d in range(self.dim)] + ["p"],
+                 Equation.euler_aeos: ["rho"] + ["v_%d" % (d + 1) for d in range(self.dim)] + ["e"],
                  Equation.shallow_water: ["h"] + ["v_%d" % (d + 1) for d in range(self.dim)]}[self.equation]
         if self.dim == 1:
             names[1] = "v"
@@ -361,7 +393,8 @@ class TimeLoop:
         mq = self.throughput(cycle, wall)
         lines = [
             "",
-            "Information: (HYP) %s" % ("Euler" if self.equation == Equation.euler else "ShallowWater"),
+            "Information: (HYP) %s" % {Equation.euler: "Euler", Equation.euler_aeos: "Euler AEOS",
+                                         Equation.shallow_water: "ShallowWater"}[self.equation],
             "  [%s %dD] with %d Qdofs on %d ranks / 1 GPU each" % (self.base_name, self.dim, self.n_dofs, self.n_ranks),
             "",
             "Job status:%s" % (" (final)" if final else ""),

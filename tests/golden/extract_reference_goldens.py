@@ -256,6 +256,12 @@ def prm_runs():
         ("euler", "verification-isentropic_vortex-2d-ssprk33-l6"),
         ("shallow_water", "verification-smooth_vortex-erk33-l6"),
         ("shallow_water", "verification-ritter_dam_break-erk33-l7"),
+        # appended (indices of the first six are referenced by tests): the euler_aeos module with the
+        # polytropic gas equation of state
+        ("euler_aeos", "verification-isentropic_vortex-pge-2d-erk33-l5"),
+        ("euler_aeos", "verification-isentropic_vortex-pge-2d-erk33-l6"),
+        ("euler_aeos", "verification-isentropic_vortex-pge-2d-ssprk33-l5"),
+        ("euler_aeos", "verification-isentropic_vortex-pge-2d-ssprk33-l6"),
     ]:
         out = read("tests/%s/%s.output" % (sub, stem))
         vals = {}
@@ -268,7 +274,7 @@ def prm_runs():
             "output": out,
             "expected": vals,
         })
-    return {"source": "tests/{euler,shallow_water}/verification-*.{prm,output}", "runs": runs}
+    return {"source": "tests/{euler,shallow_water,euler_aeos}/verification-*.{prm,output}", "runs": runs}
 
 
 dump("prm_runs.json", prm_runs())

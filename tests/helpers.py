@@ -84,28 +84,57 @@ CASES = {
     ),
 }
 
+# euler_aeos: parameters of the equation of state under the product's names (rj_equation_desc)
+AEOS_EOS = {
+    "polytropic": dict(equation_of_state=0, gamma=1.4),
+    "nasg": dict(equation_of_state=1, gamma=1.6, covolume_b=0.12, reference_pressure=0.4,
+                 reference_specific_internal_energy=0.3),
+    "vdw": dict(equation_of_state=2, gamma=1.3, covolume_b=0.1, vdw_a=0.002),
+}
+
+
+def aeos_parameters(eos, strict=True):
+    """-> (keyword arguments of rj.HyperbolicSystem, keyword arguments of the oracle's aeos_sim)"""
+    eq = dict(AEOS_EOS[eos], compute_strict_bounds=int(strict))
+    prm = dict(eq)
+    prm["eos"] = prm.pop("equation_of_state")
+    prm["compute_strict_bounds"] = bool(strict)
+    return eq, prm
+
+
+def aeos_case(name):
+    """'aeos:<eos>:<strict|loose>:<case>' -> (case, eos, strict) or None"""
+    if not name.startswith("aeos:"):
+        return None
+    _, eos, mode, case = name.split(":")
+    return case, eos, mode == "strict"
+
+
 KIND_ORACLE = {"uniform": orc.UNIFORM, "contrast": orc.CONTRAST, "isentropic_vortex": orc.ISENTROPIC_VORTEX}
 
 
 def make_mesh(case, n_cells, partition=None):
     import ryujin_b200 as rj
 
+    if aeos_case(case):
+        case = aeos_case(case)[0]
     c = CASES[case] if case in CASES else SW_CASES[case]
     return rj.CartesianMesh.rectangular_domain(c["bottom_left"], c["top_right"], n_cells, c["boundary"], partition=partition)
 
 
-def make_product(case, n_cells, device=0, comm=None, rank=0, n_ranks=1, module_params=None, **eq):
+def make_product(case, n_cells, device=0, comm=None, rank=0, n_ranks=1, module_params=None, equation="euler", partition=None,
+                 **eq):
     """-> (offline_data, module) on the GPU"""
     import ryujin_b200 as rj
 
     c = CASES[case]
-    mesh = make_mesh(case, n_cells)
+    mesh = make_mesh(case, n_cells, partition=partition)
     od = rj.OfflineData.from_mesh(mesh, rank=rank, n_ranks=n_ranks, device=device)
     iv = dict(c["iv"])
     kind = getattr(rj.InitialState, iv.pop("kind"))
     module = rj.HyperbolicModule(
         od,
-        rj.HyperbolicSystem(rj.Equation.euler, **eq),
+        rj.HyperbolicSystem(getattr(rj.Equation, equation), **eq),
         rj.InitialValues(kind, **iv),
         rj.ModuleParameters(**(module_params or {})),
         comm=comm,
@@ -113,13 +142,13 @@ def make_product(case, n_cells, device=0, comm=None, rank=0, n_ranks=1, module_p
     return od, module
 
 
-def make_oracle(oracle, case, host, off=None, **prm):
+def make_oracle(oracle, case, host, off=None, equation="euler", **prm):
     """-> (offline, sim) of the oracle on the product's arrays (or on a prepared Offline `off`)"""
     c = CASES[case]
     if off is None:
         off = oracle_offline_from_host(oracle, host)
     iv = c["iv"]
-    sim = off.euler_sim(
+    sim = (off.aeos_sim if equation == "euler_aeos" else off.euler_sim)(
         kind=KIND_ORACLE[iv["kind"]],
         direction=iv.get("direction", (1.0, 0.0, 0.0)),
         position=iv.get("position", (1.0, 0.0, 0.0)),

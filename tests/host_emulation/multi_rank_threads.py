@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import ryujin_b200 as rj  # noqa: E402
-from helpers import (CASES, SW_CASES, make_mesh, make_oracle, make_sw_oracle, make_sw_product, matching_oracle,  # noqa: E402
+from helpers import (CASES, SW_CASES, aeos_case, aeos_parameters, make_mesh, make_oracle, make_sw_oracle, make_sw_product, matching_oracle,  # noqa: E402
                      merged_partition_stencil, oracle_offline_from_partition, rel_linf, sw_bathymetry)
 
 
@@ -32,11 +32,15 @@ def build(case, n_cells, rank, world, comm, partition=None):
                                      rj.ModuleParameters(**c["mp"]), comm=comm)
         module.set_initial_precomputed(sw_bathymetry(od.host))
         return od, module
+    system = rj.HyperbolicSystem()
+    if aeos_case(case):
+        case, eos, strict = aeos_case(case)
+        system = rj.HyperbolicSystem(rj.Equation.euler_aeos, **aeos_parameters(eos, strict)[0])
     c = CASES[case]
     iv = dict(c["iv"])
     kind = getattr(rj.InitialState, iv.pop("kind"))
     od = rj.OfflineData.from_mesh(make_mesh(case, n_cells, partition), rank=rank, n_ranks=world)
-    return od, rj.HyperbolicModule(od, rj.HyperbolicSystem(), rj.InitialValues(kind, **iv), comm=comm)
+    return od, rj.HyperbolicModule(od, system, rj.InitialValues(kind, **iv), comm=comm)
 
 
 def run_rank(case, n_cells, cycles, rank, world, uid, out, ti_kw):
@@ -96,6 +100,9 @@ def oracle_n_ranks(oracle, case, n_cells, cycles, world, U0, ti_kw):
         _, sim = make_sw_oracle(oracle, case, None, off=off)
         z = np.concatenate([sw_bathymetry(h) for h in merged["hosts"]])
         sim.set_initial_precomputed(z)
+    elif aeos_case(case):
+        base, eos, strict = aeos_case(case)
+        _, sim = make_oracle(oracle, base, None, off=off, equation="euler_aeos", **aeos_parameters(eos, strict)[1])
     else:
         _, sim = make_oracle(oracle, case, None, off=off)
     ti_kw = {key: value for key, value in ti_kw.items() if key != "partition"}
@@ -132,6 +139,15 @@ def main():
             ("sod3d", [13, 7, 8], 4, dict(partition=p3), 1e-7),
             ("sod2d", [21, 19], 8, dict(partition=p2), 1e-7),
             ("sw_dam2d", [18, 17], 6, dict(partition=p2), 1e-7),
+        ]
+    if len(sys.argv) > 2 and sys.argv[2] == "aeos":
+        # euler_aeos: second precomputation cycle + exchange of the precomputed vector (the non-strict
+        # limiter reads the ghost rows' s_j), slabs and blocks
+        p2 = {2: [2, 1], 3: [3, 1], 4: [2, 2], 8: [4, 2]}[world]
+        cases = [
+            ("aeos:nasg:loose:sod2d", [24, 8 * world], 8, dict(), 1e-7),
+            ("aeos:vdw:strict:sod3d", [12, 5, 4 * world], 4, dict(), 1e-7),
+            ("aeos:polytropic:loose:sod2d", [21, 19], 6, dict(partition=p2), 1e-7),
         ]
     for case, n_cells, cycles, kw, tol in cases:
         os.environ["RYUJIN_B200_OVERLAP"] = os.environ.get("RJ_TEST_OVERLAP_MODE", "1")

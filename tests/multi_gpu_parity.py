@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import ryujin_b200 as rj  # noqa: E402
-from helpers import (CASES, SW_CASES, make_mesh, make_oracle, make_sw_oracle, make_sw_product, matching_oracle,  # noqa: E402
+from helpers import (CASES, SW_CASES, aeos_case, aeos_parameters, make_mesh, make_oracle, make_sw_oracle, make_sw_product, matching_oracle,  # noqa: E402
                      merged_partition_stencil, oracle_offline_from_partition, rel_linf, sw_bathymetry)
 
 
@@ -41,12 +41,17 @@ def run(case, n_cells, cycles, rank, world, comm, device, stepping=None, partiti
                                      rj.ModuleParameters(**c["mp"]), comm=comm)
         module.set_initial_precomputed(sw_bathymetry(od.host))
     else:
-        c = CASES[case]
+        system = rj.HyperbolicSystem()
         mesh = make_mesh(case, n_cells, partition)
+        if aeos_case(case):
+            # euler_aeos: second precomputation cycle + ghost exchange of the precomputed vector
+            case, eos, strict = aeos_case(case)
+            system = rj.HyperbolicSystem(rj.Equation.euler_aeos, **aeos_parameters(eos, strict)[0])
+        c = CASES[case]
         iv = dict(c["iv"])
         kind = getattr(rj.InitialState, iv.pop("kind"))
         od = rj.OfflineData.from_mesh(mesh, rank=rank, n_ranks=world, device=device)
-        module = rj.HyperbolicModule(od, rj.HyperbolicSystem(), rj.InitialValues(kind, **iv), comm=comm)
+        module = rj.HyperbolicModule(od, system, rj.InitialValues(kind, **iv), comm=comm)
     ti = rj.TimeIntegrator(module, rj.TimeSteppingScheme.erk_33, **ti_kw)
     if stepping is not None:
         ti.stepping = stepping
@@ -73,6 +78,9 @@ def oracle_n_ranks(oracle, case, n_cells, cycles, world, U0, ti_kw):
     if case in SW_CASES:
         _, sim = make_sw_oracle(oracle, case, None, off=off)
         sim.set_initial_precomputed(np.concatenate([sw_bathymetry(h) for h in merged["hosts"]]))
+    elif aeos_case(case):
+        base, eos, strict = aeos_case(case)
+        _, sim = make_oracle(oracle, base, None, off=off, equation="euler_aeos", **aeos_parameters(eos, strict)[1])
     else:
         _, sim = make_oracle(oracle, case, None, off=off)
     recovery = "none" if ti_kw.get("cfl_recovery_strategy") == rj.CFLRecoveryStrategy.none else "bang bang control"
@@ -103,6 +111,8 @@ def main():
         ("sod3d", [32, 8, 8 * world], 10, dict(), 1e-7),
         ("sw_dam2d", [48, 16 * world], 20, dict(), 1e-7),
         ("sw_vortex2d", [32, 16 * world], 10, dict(cfl_min=0.25, cfl_max=0.25, cfl_recovery_strategy=rj.CFLRecoveryStrategy.none), 2e-10),
+        ("aeos:nasg:loose:sod2d", [64, 16 * world], 15, dict(), 1e-7),
+        ("aeos:vdw:strict:sod3d", [32, 8, 8 * world], 8, dict(), 1e-7),
     ]
     if world in (4, 8):
         # block decompositions (BASELINE config 4: 2 x 2 x 2): face, edge and corner neighbours

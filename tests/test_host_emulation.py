@@ -23,7 +23,7 @@ EMU_LIB = os.path.join(EMU_DIR, "libryujin_b200_hostemu.so")
 # minutes-long on one host thread (66k..450k DoFs for hundreds of updates): left to the GPU
 HEAVY = ("conservation_and_symmetry or config1 or vortex_3d_cycles or golden_on_gpu "
          "or verification_goldens or decks_reproduce or config2_vortex or benchmark_size or config5_dam "
-         "or non_fma_build or device_path_equals_host or cylinder_o_grid")
+         "or non_fma_build or device_path_equals_host or cylinder_o_grid or (euler_aeos and test_cycles and sod3d)")
 
 
 def build():
@@ -115,6 +115,20 @@ def test_block_decomposition_with_ranks_as_threads():
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "multi-rank parity ok" in out.stdout
     assert out.stdout.count("vs oracle with the same partition") == 4 and "bit-identical False" not in out.stdout
+
+
+def test_euler_aeos_with_ranks_as_threads():
+    """the euler_aeos module on 3 ranks: the second precomputation cycle runs on owned rows and the
+    precomputed vector (gamma_min, s, eta of the ghost rows) travels through the halo exchange --
+    slabs and a block partition, strict and non-strict bounds, bit-identical to the oracle run on the
+    same partition"""
+    build()
+    env = dict(os.environ, RYUJIN_B200_LIB=EMU_LIB)
+    out = subprocess.run([sys.executable, os.path.join(EMU_DIR, "multi_rank_threads.py"), "3", "aeos"], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "multi-rank parity ok" in out.stdout
+    assert out.stdout.count("vs oracle with the same partition") == 3 and "bit-identical False" not in out.stdout
 
 
 def test_results_do_not_depend_on_the_block_and_thread_order():

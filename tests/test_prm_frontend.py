@@ -129,7 +129,7 @@ def test_time_loop_maps_the_sections_and_rejects_what_is_off_the_path():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("index", range(6))
+@pytest.mark.parametrize("index", range(10))
 def test_reference_decks_reproduce_their_golden_outputs(index):
     """`python -m ryujin_b200 deck.prm` on the reference's verification decks: #dofs exact, final
     time to 1e-12, normalized Linf/L1/L2 errors to 1e-8 (Ritter dam break: inside the round-off
