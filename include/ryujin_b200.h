@@ -349,6 +349,21 @@ void rj_state_destroy(rj_state *s);
 int rj_state_upload(rj_state *s, const double *host_U);
 int rj_state_download(const rj_state *s, double *host_U);
 int rj_state_download_precomputed(const rj_state *s, double *host_prec /* n_owned * n_prec */);
+/* Streaming transfers: the same copies, asynchronous, on two private copy streams (one per direction)
+ * so that they overlap with the sweeps of the module's stream; the host buffers must be page locked.
+ * (The reference keeps its vectors in host memory, multicomponent_vector.h:266 -- these calls are what
+ * a caller that owns host-side vectors uses to keep the device busy while it moves them.)
+ *   upload_begin    starts host -> staging; returns at once (waits, on the device, for the previous
+ *                   upload_end's transposition to have left the staging buffer)
+ *   upload_end      module's stream: waits for that copy, transposes into U; no host synchronisation
+ *   download_begin  module's stream: transposes U into a second staging buffer; copy stream: staging -> host
+ *   download_end    blocks the host until the data has arrived; also orders the module's stream behind it
+ * One upload and one download may be in flight per state; a second *_begin before the matching *_end is
+ * RJ_ERR_INVALID. */
+int rj_state_upload_begin(rj_state *s, const double *pinned_host_U);
+int rj_state_upload_end(rj_state *s);
+int rj_state_download_begin(rj_state *s, double *pinned_host_U);
+int rj_state_download_end(rj_state *s);
 /* U <- initial_state(x_i, t) for all owned rows (InitialValues::interpolate_hyperbolic_vector) */
 int rj_state_interpolate(rj_state *s, double t);
 double *rj_state_device_U(rj_state *s);           /* k * ld doubles  */

@@ -192,6 +192,10 @@ _SIGNATURES = {
     "rj_state_upload": (C.c_int, [vp, vp]),
     "rj_state_download": (C.c_int, [vp, vp]),
     "rj_state_download_precomputed": (C.c_int, [vp, vp]),
+    "rj_state_upload_begin": (C.c_int, [vp, vp]),
+    "rj_state_upload_end": (C.c_int, [vp]),
+    "rj_state_download_begin": (C.c_int, [vp, vp]),
+    "rj_state_download_end": (C.c_int, [vp]),
     "rj_state_interpolate": (C.c_int, [vp, C.c_double]),
     "rj_state_device_U": (vp, [vp]),
     "rj_state_device_precomputed": (vp, [vp]),

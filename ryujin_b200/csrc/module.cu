@@ -76,6 +76,14 @@ struct rj_state {
   double *U = nullptr;    /* k * ld */
   double *prec = nullptr; /* n_prec * ld */
   double *aux = nullptr;  /* n_aux * ld: per-node part of the flux contribution (1/rho, p) */
+  /* streaming transfers (rj_state_upload_begin / _end, rj_state_download_begin / _end): private AoS
+   * staging buffers and two copy streams, created on first use; not part of what swap() exchanges */
+  struct Streaming {
+    double *stage_in = nullptr, *stage_out = nullptr; /* n_owned * k each */
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t h2d_done = nullptr, in_consumed = nullptr, out_ready = nullptr, d2h_done = nullptr;
+    bool upload_pending = false, download_pending = false;
+  } *streaming = nullptr;
 };
 
 /* ------------------------------------------------------------------------ */
@@ -1947,6 +1955,22 @@ void rj_state_destroy(rj_state *s)
   cudaFree(s->U);
   cudaFree(s->prec);
   cudaFree(s->aux);
+  if (auto *x = s->streaming) {
+    if (x->h2d)
+      cudaStreamSynchronize(x->h2d);
+    if (x->d2h)
+      cudaStreamSynchronize(x->d2h);
+    cudaFree(x->stage_in);
+    cudaFree(x->stage_out);
+    for (cudaEvent_t e : {x->h2d_done, x->in_consumed, x->out_ready, x->d2h_done})
+      if (e)
+        cudaEventDestroy(e);
+    if (x->h2d)
+      cudaStreamDestroy(x->h2d);
+    if (x->d2h)
+      cudaStreamDestroy(x->d2h);
+    delete x;
+  }
   delete s;
 }
 
@@ -1978,6 +2002,105 @@ int rj_state_download(const rj_state *s, double *host_U)
     RJ_CUDA(cudaMemcpyAsync(
         host_U, hm->staging, size_t(n) * k * sizeof(double), cudaMemcpyDeviceToHost, hm->stream));
     RJ_CUDA(cudaStreamSynchronize(hm->stream));
+    return RJ_OK;
+  });
+}
+
+/* ---- streaming transfers: host <-> device copies that overlap with the sweeps ----
+ * The copies run on two private streams (one per direction: both copy engines), the transpositions
+ * AoS <-> SoA on the module's stream; events order them, the host never blocks except in
+ * rj_state_download_end().  Host buffers must be page locked. */
+static rj_state::Streaming &streaming_of(rj_state *s)
+{
+  if (!s->streaming) {
+    auto x = std::unique_ptr<rj_state::Streaming>(new rj_state::Streaming());
+    const size_t bytes = std::max<size_t>(size_t(s->hm->od->n_owned) * s->hm->k, 1) * sizeof(double);
+    RJ_CUDA(cudaMalloc(&x->stage_in, bytes));
+    RJ_CUDA(cudaMalloc(&x->stage_out, bytes));
+    RJ_CUDA(cudaStreamCreateWithFlags(&x->h2d, cudaStreamNonBlocking));
+    RJ_CUDA(cudaStreamCreateWithFlags(&x->d2h, cudaStreamNonBlocking));
+    for (cudaEvent_t *e : {&x->h2d_done, &x->in_consumed, &x->out_ready, &x->d2h_done})
+      RJ_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    s->streaming = x.release();
+  }
+  return *s->streaming;
+}
+
+int rj_state_upload_begin(rj_state *s, const double *pinned_host_U)
+{
+  return guarded([&] {
+    if (!s || !pinned_host_U)
+      throw InvalidArgument("null argument");
+    auto *hm = s->hm;
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    auto &x = streaming_of(s);
+    if (x.upload_pending)
+      throw InvalidArgument("rj_state_upload_begin: the previous upload was not completed with rj_state_upload_end");
+    /* the staging buffer is free once the previous transposition out of it has run */
+    RJ_CUDA(cudaStreamWaitEvent(x.h2d, x.in_consumed, 0));
+    RJ_CUDA(cudaMemcpyAsync(
+        x.stage_in, pinned_host_U, size_t(hm->od->n_owned) * hm->k * sizeof(double), cudaMemcpyHostToDevice, x.h2d));
+    RJ_CUDA(cudaEventRecord(x.h2d_done, x.h2d));
+    x.upload_pending = true;
+    return RJ_OK;
+  });
+}
+
+int rj_state_upload_end(rj_state *s)
+{
+  return guarded([&] {
+    if (!s)
+      throw InvalidArgument("null argument");
+    auto *hm = s->hm;
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    auto &x = streaming_of(s);
+    if (!x.upload_pending)
+      throw InvalidArgument("rj_state_upload_end without rj_state_upload_begin");
+    RJ_CUDA(cudaStreamWaitEvent(hm->stream, x.h2d_done, 0));
+    const uint32_t n = hm->od->n_owned, k = hm->k;
+    hm->launch(k_aos_to_soa, size_t(n) * k, 256, n, k, hm->od->ld, x.stage_in, s->U);
+    RJ_CUDA(cudaEventRecord(x.in_consumed, hm->stream));
+    x.upload_pending = false;
+    return RJ_OK;
+  });
+}
+
+int rj_state_download_begin(rj_state *s, double *pinned_host_U)
+{
+  return guarded([&] {
+    if (!s || !pinned_host_U)
+      throw InvalidArgument("null argument");
+    auto *hm = s->hm;
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    auto &x = streaming_of(s);
+    if (x.download_pending)
+      throw InvalidArgument("rj_state_download_begin: the previous download was not completed with rj_state_download_end");
+    const uint32_t n = hm->od->n_owned, k = hm->k;
+    hm->launch(k_soa_to_aos, size_t(n) * k, 256, n, k, hm->od->ld, s->U, x.stage_out);
+    RJ_CUDA(cudaEventRecord(x.out_ready, hm->stream));
+    RJ_CUDA(cudaStreamWaitEvent(x.d2h, x.out_ready, 0));
+    RJ_CUDA(cudaMemcpyAsync(pinned_host_U, x.stage_out, size_t(n) * k * sizeof(double), cudaMemcpyDeviceToHost, x.d2h));
+    RJ_CUDA(cudaEventRecord(x.d2h_done, x.d2h));
+    x.download_pending = true;
+    return RJ_OK;
+  });
+}
+
+int rj_state_download_end(rj_state *s)
+{
+  return guarded([&] {
+    if (!s)
+      throw InvalidArgument("null argument");
+    auto *hm = s->hm;
+    RJ_CUDA(cudaSetDevice(hm->od->device));
+    auto &x = streaming_of(s);
+    if (!x.download_pending)
+      throw InvalidArgument("rj_state_download_end without rj_state_download_begin");
+    /* the module's stream is ordered behind the copy as well (the staging buffer is reused by the
+     * next rj_state_download_begin; an event recorded on the stream afterwards includes the copy) */
+    RJ_CUDA(cudaStreamWaitEvent(hm->stream, x.d2h_done, 0));
+    RJ_CUDA(cudaEventSynchronize(x.d2h_done));
+    x.download_pending = false;
     return RJ_OK;
   });
 }

@@ -194,6 +194,19 @@ class StateVector:
     def download_to_pointer(self, host_ptr):
         check(lib.rj_state_download(self._h, host_ptr))
 
+    # streaming transfers (page-locked host memory; overlap with the sweeps of the module's stream)
+    def upload_begin(self, host_ptr):
+        check(lib.rj_state_upload_begin(self._h, host_ptr))
+
+    def upload_end(self):
+        check(lib.rj_state_upload_end(self._h))
+
+    def download_begin(self, host_ptr):
+        check(lib.rj_state_download_begin(self._h, host_ptr))
+
+    def download_end(self):
+        check(lib.rj_state_download_end(self._h))
+
     def download_precomputed(self):
         out = np.zeros((self.module.n_owned, self.module.n_precomputed))
         check(lib.rj_state_download_precomputed(self._h, out.ctypes.data))

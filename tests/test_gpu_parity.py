@@ -582,3 +582,67 @@ def test_profiling_and_raw_pointer_transfers_do_not_change_results():
     # 4 ERK33 cycles = 12 updates: one launch of every sweep per update
     for name in ("dij", "alpha", "low_order", "pij_lij", "high_order_next_lij", "high_order_final", "precompute"):
         assert on[name][1] == 12 and on[name][0] > 0.0, (name, on[name])
+
+
+def test_streaming_transfers_match_the_blocking_ones():
+    """`rj_state_upload_begin/_end`, `rj_state_download_begin/_end` (bench.py's end-to-end pipeline: the
+    copies of step n+1 / n-1 run on the copy streams while step n computes): same bits as the blocking
+    transfers, and the begin/end protocol is enforced"""
+    import ryujin_b200 as rj
+
+    def host_buffer(shape):
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                t = torch.zeros(shape, dtype=torch.float64).pin_memory()
+                return t, t.numpy(), t.data_ptr()
+        except ImportError:
+            pass
+        a = np.zeros(shape)
+        return a, a, a.ctypes.data
+
+    od, module = make_product("sod2d", [32, 12])
+    ti = rj.TimeIntegrator(module)
+    state = module.state_vector()
+    state.interpolate(0.0)
+    U0 = np.ascontiguousarray(state.download())
+    n_steps = 4
+
+    # blocking: every step starts from a fresh upload of its own input (input n = U0 * (1 + n/16))
+    inputs = [U0 * (1.0 + n / 16.0) for n in range(n_steps)]
+    expected, taus = [], []
+    for n in range(n_steps):
+        state.upload(inputs[n])
+        taus.append(ti.step(state, 0.0))
+        expected.append(state.download().copy())
+
+    keep_in, in_np, in_ptr = zip(*[host_buffer(U0.shape) for _ in range(2)])
+    keep_out, out_np, out_ptr = zip(*[host_buffer(U0.shape) for _ in range(2)])
+    got = []
+    in_np[0][...] = inputs[0]
+    state.upload_begin(in_ptr[0])
+    for n in range(n_steps):
+        state.upload_end()
+        if n + 1 < n_steps:
+            in_np[(n + 1) % 2][...] = inputs[n + 1]
+            state.upload_begin(in_ptr[(n + 1) % 2])
+        assert ti.step(state, 0.0) == taus[n]
+        if n > 0:
+            state.download_end()
+            got.append(out_np[(n - 1) % 2].copy())
+        state.download_begin(out_ptr[n % 2])
+    state.download_end()
+    got.append(out_np[(n_steps - 1) % 2].copy())
+    for n in range(n_steps):
+        assert np.array_equal(got[n], expected[n]), n
+
+    with pytest.raises(Exception):
+        state.upload_end()
+    with pytest.raises(Exception):
+        state.download_end()
+    state.upload_begin(in_ptr[0])
+    with pytest.raises(Exception):
+        state.upload_begin(in_ptr[1])
+    state.upload_end()
+    module.synchronize()
