@@ -39,6 +39,7 @@ namespace rjb
     static constexpr bool aeos = false;
     static constexpr bool have_source_terms = false;
     static constexpr bool have_high_order_flux = false;
+    static constexpr bool edge_cache = true; /* kernels.cuh: RJ_EDGE_CACHE */
     using Params = EulerParams;
 
     /* ---------------- HyperbolicSystemView ---------------- */
@@ -520,6 +521,19 @@ namespace rjb
 
     /* ---------------- Limiter ---------------- */
 
+    /* The one quantity of Limiter::accumulate that is symmetric in (i, j): the specific entropy of the
+     * midpoint state, limiter.h:314-319.  (U_i + U_j) * .5 == (U_j + U_i) * .5 bit for bit; on the diagonal
+     * (U_i + U_i) * .5 == U_i exactly, whose specific entropy is the precomputed s_i. */
+    RJ_DEVICE static double edge_value(const Params &p, const double (&U_i)[k], const double (&U_j)[k])
+    {
+      double U_mid[k];
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        U_mid[q] = (U_i[q] + U_j[q]) * .5;
+      return specific_entropy(p, U_mid);
+    }
+    RJ_DEVICE static double edge_value_diagonal(const double (&prec_i)[n_prec]) { return prec_i[0]; }
+
     struct LimiterAccumulator {
       double rho_min, rho_max, s_min;
       double rho_relaxation_numerator, rho_relaxation_denominator, s_interp_max;
@@ -557,6 +571,27 @@ namespace rjb
         for (int q = 0; q < k; ++q)
           U_mid[q] = (U_i[q] + U_j[q]) * .5;
         const double s_interp = specific_entropy(p, U_mid);
+        s_interp_max = fmax(s_interp_max, s_interp);
+      }
+
+      /* the same with s_interp = edge_value(U_i, U_j) taken from the edge cache */
+      RJ_DEVICE void accumulate_cached(const double (&U_i)[k],
+                                       const double (&U_j)[k],
+                                       const double (&prec_j)[n_prec],
+                                       const double (&scaled_c_ij)[dim],
+                                       const double s_interp)
+      {
+        const double s_j = prec_j[0];
+        double dmc = (U_i[1] - U_j[1]) * scaled_c_ij[0];
+#pragma unroll
+        for (int d = 1; d < dim; ++d)
+          dmc += (U_i[1 + d] - U_j[1 + d]) * scaled_c_ij[d];
+        const double rho_ij_bar = 0.5 * (U_i[0] + U_j[0] + dmc);
+        rho_min = fmin(rho_min, rho_ij_bar);
+        rho_max = fmax(rho_max, rho_ij_bar);
+        s_min = fmin(s_min, s_j);
+        rho_relaxation_numerator += (U_i[0] + U_j[0]);
+        rho_relaxation_denominator += 1.;
         s_interp_max = fmax(s_interp_max, s_interp);
       }
 

@@ -42,6 +42,7 @@ namespace rjb
     static constexpr bool aeos = true;
     static constexpr bool have_source_terms = false;
     static constexpr bool have_high_order_flux = false;
+    static constexpr bool edge_cache = false; /* its midpoint entropy depends on gamma_min of row i */
     using Params = EulerAeosParams;
 
     /* ---------------- equation of state ---------------- */

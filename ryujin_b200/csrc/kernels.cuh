@@ -72,6 +72,22 @@
 #ifndef RJ_DIJ_W
 #define RJ_DIJ_W 4 /* warps per slice of the edge-parallel d_ij kernel */
 #endif
+/* Edge cache: quantities of the sweep that are symmetric in (i, j) are evaluated once per edge by the
+ * edge-parallel kernel of step 2 (which already holds U_i and U_j and already mirrors d_ij) instead of
+ * twice by the row-parallel step 4.  For the polytropic Euler limiter that is the specific entropy of
+ * the midpoint state (one pow + one division per stencil entry, limiter.h:314-319): (U_i + U_j) * .5 is
+ * the same state in row i and in row j bit for bit, so are the cached values.
+ *   0: off (step 4 evaluates it per entry)   1: inside k_dij   2: the same kernel body, launched on its own
+ *   3: inside k_alpha (row parallel, entries j > i, mirrored) */
+#ifndef RJ_EDGE_CACHE
+#define RJ_EDGE_CACHE 0
+#endif
+#ifndef RJ_MB_EC
+#define RJ_MB_EC 8
+#endif
+#ifndef RJ_DIJ_RELOAD
+#define RJ_DIJ_RELOAD 0
+#endif
 #ifndef RJ_MB_ALPHA
 #define RJ_MB_ALPHA 8
 #endif
@@ -173,9 +189,9 @@ namespace rjb
     uint32_t i, len, width, base;
   };
 
-  RJ_DEVICE bool row_info(const StencilView &v, uint32_t row_begin, uint32_t row_end, RowInfo &r)
+  RJ_DEVICE bool row_info(const uint32_t vblock, const StencilView &v, uint32_t row_begin, uint32_t row_end, RowInfo &r)
   {
-    r.i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    r.i = row_begin + vblock * blockDim.x + threadIdx.x;
     if (r.i >= row_end)
       return false;
     const uint32_t g = r.i >> 5;
@@ -192,22 +208,23 @@ namespace rjb
    * One thread per boundary DoF; entries of a DoF are applied in stored order.
    * ---------------------------------------------------------------------- */
   template <class Eq, class IV>
-  __global__ void k_apply_boundary_conditions(uint32_t n_groups,
-                                              const uint32_t *__restrict__ group_dof,
-                                              const uint32_t *__restrict__ group_start,
-                                              const double *__restrict__ bnormal,
-                                              const double *__restrict__ bposition,
-                                              const int32_t *__restrict__ bid,
-                                              uint32_t ld,
-                                              typename Eq::Params prm,
-                                              IV iv,
-                                              double t_host,
-                                              const CycleScalars *__restrict__ cycle,
-                                              double tau_factor,
-                                              double *__restrict__ U)
+  RJ_DEVICE void apply_boundary_conditions_body(const uint32_t vblock,
+                                                uint32_t n_groups,
+                                                const uint32_t *__restrict__ group_dof,
+                                                const uint32_t *__restrict__ group_start,
+                                                const double *__restrict__ bnormal,
+                                                const double *__restrict__ bposition,
+                                                const int32_t *__restrict__ bid,
+                                                uint32_t ld,
+                                                typename Eq::Params prm,
+                                                IV iv,
+                                                double t_host,
+                                                const CycleScalars *__restrict__ cycle,
+                                                double tau_factor,
+                                                double *__restrict__ U)
   {
     constexpr int k = Eq::k, dim = Eq::dim;
-    const uint32_t gidx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gidx = vblock * blockDim.x + threadIdx.x;
     if (gidx >= n_groups)
       return;
     /* t + c * tau exactly as the host computes it (time_integrator.template.h:380,395) */
@@ -230,6 +247,12 @@ namespace rjb
           prm, id, U_i, normal, [&](double(&D)[k]) { iv.template initial_state<Eq>(prm, position, t, D); });
     }
     store_state<k>(U, ld, i, U_i);
+  }
+
+  template <class Eq, class IV>
+  __global__ void k_apply_boundary_conditions(uint32_t n_groups, const uint32_t *__restrict__ group_dof, const uint32_t *__restrict__ group_start, const double *__restrict__ bnormal, const double *__restrict__ bposition, const int32_t *__restrict__ bid, uint32_t ld, typename Eq::Params prm, IV iv, double t_host, const CycleScalars *__restrict__ cycle, double tau_factor, double *__restrict__ U)
+  {
+    apply_boundary_conditions_body<Eq, IV>(blockIdx.x, n_groups, group_dof, group_start, bnormal, bposition, bid, ld, prm, iv, t_host, cycle, tau_factor, U);
   }
 
 
@@ -262,20 +285,21 @@ namespace rjb
    * euler/hyperbolic_system.h:705-737.
    * ---------------------------------------------------------------------- */
   template <class Eq>
-  __global__ void k_precompute(StencilView v,
-                               typename Eq::Params prm,
-                               uint32_t row_begin,
-                               uint32_t row_end,
-                               const double *__restrict__ U,
-                               const double *__restrict__ initial_precomputed,
-                               double *__restrict__ prec,
-                               double *__restrict__ aux)
+  RJ_DEVICE void precompute_body(const uint32_t vblock,
+                                 StencilView v,
+                                 typename Eq::Params prm,
+                                 uint32_t row_begin,
+                                 uint32_t row_end,
+                                 const double *__restrict__ U,
+                                 const double *__restrict__ initial_precomputed,
+                                 double *__restrict__ prec,
+                                 double *__restrict__ aux)
   {
     /* owned rows as in the reference; ghost rows are recomputed locally from the
      * exchanged ghost state (bit-identical to the owner's values), which replaces
      * the ghost exchange of the precomputed vector (C2, :157-160) */
     constexpr int k = Eq::k, np = Eq::n_prec, na = Eq::n_aux;
-    const uint32_t i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = row_begin + vblock * blockDim.x + threadIdx.x;
     if (i >= row_end)
       return;
     if (i < v.n_owned && v.row_length[i] <= 1)
@@ -293,6 +317,12 @@ namespace rjb
     store_state<na>(aux, v.ld, i, aux_i);
   }
 
+  template <class Eq>
+  __global__ void k_precompute(StencilView v, typename Eq::Params prm, uint32_t row_begin, uint32_t row_end, const double *__restrict__ U, const double *__restrict__ initial_precomputed, double *__restrict__ prec, double *__restrict__ aux)
+  {
+    precompute_body<Eq>(blockIdx.x, v, prm, row_begin, row_end, U, initial_precomputed, prec, aux);
+  }
+
 
   /* Second precomputation cycle of equations that have one (euler_aeos/hyperbolic_system.h:
    * 943-973): gamma_min_i = min over the stencil of the surrogate gamma of (U_j, p_j), then the
@@ -300,16 +330,17 @@ namespace rjb
    * precomputed vector is exchanged afterwards, as the reference does between its cycles.  Reads
    * component 0 of other rows, writes components 1.. of its own row: no hazard within the launch. */
   template <class Eq>
-  __global__ void __launch_bounds__(128) k_precompute_stencil(StencilView v,
-                                                              typename Eq::Params prm,
-                                                              uint32_t row_begin,
-                                                              uint32_t row_end,
-                                                              const double *__restrict__ U,
-                                                              double *prec)
+  RJ_DEVICE void precompute_stencil_body(const uint32_t vblock,
+                                         StencilView v,
+                                         typename Eq::Params prm,
+                                         uint32_t row_begin,
+                                         uint32_t row_end,
+                                         const double *__restrict__ U,
+                                         double *prec)
   {
     constexpr int k = Eq::k, np = Eq::n_prec;
     RowInfo r;
-    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+    if (!row_info(vblock, v, row_begin, row_end, r) || r.len <= 1)
       return;
     const uint32_t i = r.i;
     double U_i[k], prec_i[np];
@@ -330,6 +361,12 @@ namespace rjb
       prec[size_t(q) * v.ld + i] = prec_i[q];
   }
 
+  template <class Eq>
+  __global__ void __launch_bounds__(128) k_precompute_stencil(StencilView v, typename Eq::Params prm, uint32_t row_begin, uint32_t row_end, const double *__restrict__ U, double *prec)
+  {
+    precompute_stencil_body<Eq>(blockIdx.x, v, prm, row_begin, row_end, U, prec);
+  }
+
 
   /* ---------------------------------------------------------------------- *
    * Step 2: off-diagonal d_ij for j > i and alpha_i,
@@ -345,17 +382,19 @@ namespace rjb
    *  k_alpha ROW parallel: the entropy-viscosity commutator, accumulated in
    *          column order in one thread as the reference does.
    * ---------------------------------------------------------------------- */
-  template <class Eq, int W>
-  __global__ void __launch_bounds__(32 * W, RJ_MB_DIJ) k_dij(StencilView v,
-                                                             typename Eq::Params prm,
-                                                             uint32_t slice_begin,
-                                                             uint32_t slice_end,
-                                                             const double *__restrict__ U,
-                                                             const double *__restrict__ prec,
-                                                             double *__restrict__ dij)
+  template <class Eq, int W, bool do_dij, bool do_cache>
+  RJ_DEVICE void dij_body(const uint32_t vblock,
+                          StencilView v,
+                          typename Eq::Params prm,
+                          uint32_t slice_begin,
+                          uint32_t slice_end,
+                          const double *__restrict__ U,
+                          const double *__restrict__ prec,
+                          double *__restrict__ dij,
+                          double *__restrict__ edge_cache)
   {
     constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec;
-    const uint32_t g = slice_begin + blockIdx.x;
+    const uint32_t g = slice_begin + vblock;
     if (g >= slice_end)
       return;
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -367,56 +406,94 @@ namespace rjb
       return;
     const uint32_t base = v.slice_offsets[g] + lane;
 
+#if !RJ_DIJ_RELOAD
     double U_i[k], prec_i[np];
     load_state<k>(U, v.ld, i, U_i);
     load_state<np>(prec, v.ld, i, prec_i);
+#endif
 
     for (uint32_t col = w; col < len; col += W) {
-      if (col == 0)
+      if (col == 0) {
+        if constexpr (do_cache) {
+          double prec_d[np];
+          load_state<np>(prec, v.ld, i, prec_d);
+          edge_cache[base] = Eq::edge_value_diagonal(prec_d);
+        }
         continue;
+      }
       const uint32_t e = base + col * 32;
       const uint32_t j = v.cols[e];
       if (j < i)
         continue;
-      double U_j[k], prec_j[np], c_ij[dim];
+#if RJ_DIJ_RELOAD
+      /* experiment: the row's own state is re-read per solve (volatile: not hoisted) instead of being
+       * kept in registers across the Riemann solves */
+      double U_i[k], prec_i[np];
+#pragma unroll
+      for (int q = 0; q < k; ++q)
+        U_i[q] = *(const volatile double *)&U[size_t(q) * v.ld + i];
+#pragma unroll
+      for (int q = 0; q < np; ++q)
+        prec_i[q] = *(const volatile double *)&prec[size_t(q) * v.ld + i];
+#endif
+      double U_j[k], prec_j[np];
       load_state<k>(U, v.ld, j, U_j);
       load_state<np>(prec, v.ld, j, prec_j);
-#pragma unroll
-      for (int d = 0; d < dim; ++d)
-        c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
-
-      double nrm2 = c_ij[0] * c_ij[0];
-#pragma unroll
-      for (int d = 1; d < dim; ++d)
-        nrm2 += c_ij[d] * c_ij[d];
-      const double nrm = sqrt(nrm2);
-      const double inv = 1. / nrm;
-      double n_ij[dim];
-#pragma unroll
-      for (int d = 0; d < dim; ++d)
-        n_ij[d] = c_ij[d] * inv;
-      const double lambda_max = Eq::riemann_lambda_max(prm, U_i, prec_i, U_j, prec_j, n_ij);
-      const double d_ij = nrm * lambda_max;
-      dij[e] = d_ij;
       const uint32_t eT = v.transposed[e];
-      if (eT < v.E_owned)
-        dij[eT] = d_ij;
+
+      if constexpr (do_cache) {
+        const double value = Eq::edge_value(prm, U_i, U_j);
+        edge_cache[e] = value;
+        if (eT < v.E_owned)
+          edge_cache[eT] = value;
+      }
+
+      if constexpr (do_dij) {
+        double c_ij[dim];
+#pragma unroll
+        for (int d = 0; d < dim; ++d)
+          c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
+
+        double nrm2 = c_ij[0] * c_ij[0];
+#pragma unroll
+        for (int d = 1; d < dim; ++d)
+          nrm2 += c_ij[d] * c_ij[d];
+        const double nrm = sqrt(nrm2);
+        const double inv = 1. / nrm;
+        double n_ij[dim];
+#pragma unroll
+        for (int d = 0; d < dim; ++d)
+          n_ij[d] = c_ij[d] * inv;
+        const double lambda_max = Eq::riemann_lambda_max(prm, U_i, prec_i, U_j, prec_j, n_ij);
+        const double d_ij = nrm * lambda_max;
+        dij[e] = d_ij;
+        if (eT < v.E_owned)
+          dij[eT] = d_ij;
+      }
     }
   }
 
-  template <class Eq>
-  __global__ void __launch_bounds__(128, RJ_MB_ALPHA) k_alpha(StencilView v,
-                                                              typename Eq::Params prm,
-                                                              uint32_t row_begin,
-                                                              uint32_t row_end,
-                                                              const double *__restrict__ U,
-                                                              const double *__restrict__ prec,
-                                                              const double *__restrict__ aux,
-                                                              double *__restrict__ alpha)
+  template <class Eq, int W, bool do_dij = true, bool do_cache = false>
+  __global__ void __launch_bounds__(32 * W, do_dij ? RJ_MB_DIJ : RJ_MB_EC) k_dij(StencilView v, typename Eq::Params prm, uint32_t slice_begin, uint32_t slice_end, const double *__restrict__ U, const double *__restrict__ prec, double *__restrict__ dij, double *__restrict__ edge_cache)
+  {
+    dij_body<Eq, W, do_dij, do_cache>(blockIdx.x, v, prm, slice_begin, slice_end, U, prec, dij, edge_cache);
+  }
+
+  template <class Eq, bool do_cache>
+  RJ_DEVICE void alpha_body(const uint32_t vblock,
+                            StencilView v,
+                            typename Eq::Params prm,
+                            uint32_t row_begin,
+                            uint32_t row_end,
+                            const double *__restrict__ U,
+                            const double *__restrict__ prec,
+                            const double *__restrict__ aux,
+                            double *__restrict__ alpha,
+                            double *__restrict__ edge_cache)
   {
     constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec, na = Eq::n_aux;
     RowInfo r;
-    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+    if (!row_info(vblock, v, row_begin, row_end, r) || r.len <= 1)
       return;
     const uint32_t i = r.i;
 
@@ -440,31 +517,51 @@ namespace rjb
       for (int d = 0; d < dim; ++d)
         c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
       indicator.accumulate(prm, U_i, prec_i, U_j, prec_j, Eq::load_aux(aux_j), c_ij);
+      if constexpr (do_cache) {
+        /* RJ_EDGE_CACHE == 3: the symmetric edge quantity of step 4 is evaluated here, in the shadow of
+         * the gather latency this sweep is bound by, for j > i, and mirrored (as k_dij mirrors d_ij) */
+        if (col == 0)
+          edge_cache[e] = Eq::edge_value_diagonal(prec_i);
+        else if (j > i) {
+          const double value = Eq::edge_value(prm, U_i, U_j);
+          edge_cache[e] = value;
+          const uint32_t eT = v.transposed[e];
+          if (eT < v.E_owned)
+            edge_cache[eT] = value;
+        }
+      }
     }
 
     const double hd_i = v.mi[i] * v.measure_of_omega_inverse;
     alpha[i] = indicator.alpha(prm, hd_i);
   }
 
+  template <class Eq, bool do_cache = false>
+  __global__ void __launch_bounds__(128, RJ_MB_ALPHA) k_alpha(StencilView v, typename Eq::Params prm, uint32_t row_begin, uint32_t row_end, const double *__restrict__ U, const double *__restrict__ prec, const double *__restrict__ aux, double *__restrict__ alpha, double *__restrict__ edge_cache)
+  {
+    alpha_body<Eq, do_cache>(blockIdx.x, v, prm, row_begin, row_end, U, prec, aux, alpha, edge_cache);
+  }
+
 
   /* Step 3a: complete d_ij on coupling boundary pairs (i < j),
    * hyperbolic_module.template.h:461-490. */
   template <class Eq>
-  __global__ void k_boundary_dij(uint32_t n_pairs,
-                                 const uint32_t *__restrict__ pair_i,
-                                 const uint32_t *__restrict__ pair_j,
-                                 const uint32_t *__restrict__ pair_e,
-                                 const uint32_t *__restrict__ pair_eT,
-                                 const double *__restrict__ pair_cji,
-                                 uint32_t ld,
-                                 uint32_t E_owned,
-                                 typename Eq::Params prm,
-                                 const double *__restrict__ U,
-                                 const double *__restrict__ prec,
-                                 double *__restrict__ dij)
+  RJ_DEVICE void boundary_dij_body(const uint32_t vblock,
+                                   uint32_t n_pairs,
+                                   const uint32_t *__restrict__ pair_i,
+                                   const uint32_t *__restrict__ pair_j,
+                                   const uint32_t *__restrict__ pair_e,
+                                   const uint32_t *__restrict__ pair_eT,
+                                   const double *__restrict__ pair_cji,
+                                   uint32_t ld,
+                                   uint32_t E_owned,
+                                   typename Eq::Params prm,
+                                   const double *__restrict__ U,
+                                   const double *__restrict__ prec,
+                                   double *__restrict__ dij)
   {
     constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = vblock * blockDim.x + threadIdx.x;
     if (p >= n_pairs)
       return;
     const uint32_t i = pair_i[p], j = pair_j[p], e = pair_e[p], eT = pair_eT[p];
@@ -495,20 +592,27 @@ namespace rjb
       dij[eT] = d;
   }
 
+  template <class Eq>
+  __global__ void k_boundary_dij(uint32_t n_pairs, const uint32_t *__restrict__ pair_i, const uint32_t *__restrict__ pair_j, const uint32_t *__restrict__ pair_e, const uint32_t *__restrict__ pair_eT, const double *__restrict__ pair_cji, uint32_t ld, uint32_t E_owned, typename Eq::Params prm, const double *__restrict__ U, const double *__restrict__ prec, double *__restrict__ dij)
+  {
+    boundary_dij_body<Eq>(blockIdx.x, n_pairs, pair_i, pair_j, pair_e, pair_eT, pair_cji, ld, E_owned, prm, U, prec, dij);
+  }
+
 
   /* Step 3b: diagonal d_ii and tau_max, hyperbolic_module.template.h:494-560.
    * The row sum runs in column order in one thread; only the minimum over
    * rows (order independent) uses shuffles + one atomicMin per block. */
-  __global__ void k_dii_tau(StencilView v,
-                            uint32_t row_begin,
-                            uint32_t row_end,
-                            double cfl,
-                            double *__restrict__ dij,
-                            StepScalars *__restrict__ scalars)
+  RJ_DEVICE void dii_tau_body(const uint32_t vblock,
+                              StencilView v,
+                              uint32_t row_begin,
+                              uint32_t row_end,
+                              double cfl,
+                              double *__restrict__ dij,
+                              StepScalars *__restrict__ scalars)
   {
     RowInfo r;
     double tau_i = DBL_MAX;
-    if (row_info(v, row_begin, row_end, r) && r.len > 1) {
+    if (row_info(vblock, v, row_begin, row_end, r) && r.len > 1) {
       double d_sum = 0.;
     RJ_UNROLL(RJ_UNROLL_DII)
       for (uint32_t col = 1; col < r.len; ++col)
@@ -541,6 +645,11 @@ namespace rjb
       if (lane == 0)
         atomicMin(&scalars->tau_max_bits, bits);
     }
+  }
+
+  __global__ void k_dii_tau(StencilView v, uint32_t row_begin, uint32_t row_end, double cfl, double *__restrict__ dij, StepScalars *__restrict__ scalars)
+  {
+    dii_tau_body(blockIdx.x, v, row_begin, row_end, cfl, dij, scalars);
   }
 
   __global__ void k_reset_scalars(StepScalars *s)
@@ -602,28 +711,31 @@ namespace rjb
   /* (Running this sweep as two lighter kernels -- update + bounds, r_i + P_ij -- was measured in
    * round 1 and rejected: 9.6-11.0 ms instead of 7.0 ms, both halves re-read c_ij, d_ij, U_j.) */
   template <class Eq, int stages>
-  __global__ void __launch_bounds__(128, Eq::shallow_water ? RJ_MB_LOW_SW : RJ_MB_LOW) k_low_order(StencilView v,
-                                                     typename Eq::Params prm,
-                                                     uint32_t row_begin,
-                                                     uint32_t row_end,
-                                                     const double *__restrict__ U,
-                                                     const double *__restrict__ prec,
-                                                     const double *__restrict__ aux,
-                                                     StagePointers<stages> st,
-                                                     const double *__restrict__ alpha,
-                                                     const double *__restrict__ dij,
-                                                     const StepScalars *__restrict__ scalars,
-                                                     double *__restrict__ U_new,
-                                                     double *__restrict__ r_vec,
-                                                     double *__restrict__ bounds,
-                                                     double *__restrict__ pij)
+  RJ_DEVICE void low_order_body(const uint32_t vblock,
+                                const double tau,
+                                StencilView v,
+                                typename Eq::Params prm,
+                                uint32_t row_begin,
+                                uint32_t row_end,
+                                const double *__restrict__ U,
+                                const double *__restrict__ prec,
+                                const double *__restrict__ aux,
+                                StagePointers<stages> st,
+                                const double *__restrict__ alpha,
+                                const double *__restrict__ dij,
+                                const double *__restrict__ edge_cache,
+                                double *__restrict__ U_new,
+                                double *__restrict__ r_vec,
+                                double *__restrict__ bounds,
+                                double *__restrict__ pij)
   {
     constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec, nb = Eq::n_bounds, na = Eq::n_aux;
+    constexpr bool cached = Eq::edge_cache && (RJ_EDGE_CACHE != 0);
     RowInfo r;
-    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+    if (!row_info(vblock, v, row_begin, row_end, r) || r.len <= 1)
       return;
     const uint32_t i = r.i;
-    const double tau = scalars->tau;
+    
 
     double weight = -1.;
 #pragma unroll
@@ -780,6 +892,8 @@ namespace rjb
         }
         if constexpr (Eq::aeos)
           limiter.accumulate(prm, U_i, flux_i, U_j, flux_j, prec_j, scaled_c_ij);
+        else if constexpr (cached)
+          limiter.accumulate_cached(U_i, U_j, prec_j, scaled_c_ij, edge_cache[e]);
         else
           limiter.accumulate(prm, U_i, U_j, prec_j, scaled_c_ij);
       }
@@ -860,29 +974,37 @@ namespace rjb
     store_state<nb>(bounds, v.ld, i, b);
   }
 
+  template <class Eq, int stages>
+  __global__ void __launch_bounds__(128, Eq::shallow_water ? RJ_MB_LOW_SW : RJ_MB_LOW) k_low_order(StencilView v, typename Eq::Params prm, uint32_t row_begin, uint32_t row_end, const double *__restrict__ U, const double *__restrict__ prec, const double *__restrict__ aux, StagePointers<stages> st, const double *__restrict__ alpha, const double *__restrict__ dij, const double *__restrict__ edge_cache, const StepScalars *__restrict__ scalars, double *__restrict__ U_new, double *__restrict__ r_vec, double *__restrict__ bounds, double *__restrict__ pij)
+  {
+    low_order_body<Eq, stages>(blockIdx.x, scalars->tau, v, prm, row_begin, row_end, U, prec, aux, st, alpha, dij, edge_cache, U_new, r_vec, bounds, pij);
+  }
+
 
   /* ---------------------------------------------------------------------- *
    * Step 5: mass-matrix correction of P_ij and first l_ij,
    * hyperbolic_module.template.h:892-1041.
    * ---------------------------------------------------------------------- */
   template <class Eq>
-  __global__ void __launch_bounds__(128, RJ_MB_PIJ) k_pij_lij(StencilView v,
-                                                   typename Eq::Params prm,
-                                                   uint32_t row_begin,
-                                                   uint32_t row_end,
-                                                   const double *__restrict__ U_new,
-                                                   const double *__restrict__ r_vec,
-                                                   const double *__restrict__ bounds,
-                                                   StepScalars *__restrict__ scalars,
-                                                   double *__restrict__ pij,
-                                                   double *__restrict__ lij)
+  RJ_DEVICE void pij_lij_body(const uint32_t vblock,
+                              const double tau,
+                              StencilView v,
+                              typename Eq::Params prm,
+                              uint32_t row_begin,
+                              uint32_t row_end,
+                              const double *__restrict__ U_new,
+                              const double *__restrict__ r_vec,
+                              const double *__restrict__ bounds,
+                              StepScalars *__restrict__ scalars,
+                              double *__restrict__ pij,
+                              double *__restrict__ lij)
   {
     constexpr int k = Eq::k, nb = Eq::n_bounds;
     RowInfo r;
-    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+    if (!row_info(vblock, v, row_begin, row_end, r) || r.len <= 1)
       return;
     const uint32_t i = r.i;
-    const double tau = scalars->tau;
+    
 
     double b[nb], U_i_new[k], F_iH[k];
     load_state<nb>(bounds, v.ld, i, b);
@@ -926,25 +1048,32 @@ namespace rjb
       atomicOr(&scalars->restart_needed, 1);
   }
 
+  template <class Eq>
+  __global__ void __launch_bounds__(128, RJ_MB_PIJ) k_pij_lij(StencilView v, typename Eq::Params prm, uint32_t row_begin, uint32_t row_end, const double *__restrict__ U_new, const double *__restrict__ r_vec, const double *__restrict__ bounds, StepScalars *__restrict__ scalars, double *__restrict__ pij, double *__restrict__ lij)
+  {
+    pij_lij_body<Eq>(blockIdx.x, scalars->tau, v, prm, row_begin, row_end, U_new, r_vec, bounds, scalars, pij, lij);
+  }
+
 
   /* ---------------------------------------------------------------------- *
    * Steps 6, 7: symmetrize l_ij, high-order update, next l_ij,
    * hyperbolic_module.template.h:1053-1182.
    * ---------------------------------------------------------------------- */
   template <class Eq, bool last_round>
-  __global__ void __launch_bounds__(128, RJ_MB_HO) k_high_order(StencilView v,
-                                                      typename Eq::Params prm,
-                                                      uint32_t row_begin,
-                                                      uint32_t row_end,
-                                                      const double *__restrict__ bounds,
-                                                      const double *__restrict__ pij,
-                                                      const double *__restrict__ lij,
-                                                      double *__restrict__ lij_next,
-                                                      double *__restrict__ U_new)
+  RJ_DEVICE void high_order_body(const uint32_t vblock,
+                                 StencilView v,
+                                 typename Eq::Params prm,
+                                 uint32_t row_begin,
+                                 uint32_t row_end,
+                                 const double *__restrict__ bounds,
+                                 const double *__restrict__ pij,
+                                 const double *__restrict__ lij,
+                                 double *__restrict__ lij_next,
+                                 double *__restrict__ U_new)
   {
     constexpr int k = Eq::k, nb = Eq::n_bounds;
     RowInfo r;
-    if (!row_info(v, row_begin, row_end, r) || r.len <= 1)
+    if (!row_info(vblock, v, row_begin, row_end, r) || r.len <= 1)
       return;
     const uint32_t i = r.i;
 
@@ -986,6 +1115,12 @@ namespace rjb
     }
   }
 
+  template <class Eq, bool last_round>
+  __global__ void __launch_bounds__(128, RJ_MB_HO) k_high_order(StencilView v, typename Eq::Params prm, uint32_t row_begin, uint32_t row_end, const double *__restrict__ bounds, const double *__restrict__ pij, const double *__restrict__ lij, double *__restrict__ lij_next, double *__restrict__ U_new)
+  {
+    high_order_body<Eq, last_round>(blockIdx.x, v, prm, row_begin, row_end, bounds, pij, lij, lij_next, U_new);
+  }
+
 
   /* ---------------------------------------------------------------------- *
    * Postprocessor (source/postprocessor.template.h:113-281): schlieren |sum_j c_ij q_j| / m_i of a
@@ -1019,7 +1154,7 @@ namespace rjb
     RowInfo r;
     double value = 0.;
     bool active = false;
-    if (row_info(v, row_begin, row_end, r) && r.len > 1) {
+    if (row_info(blockIdx.x, v, row_begin, row_end, r) && r.len > 1) {
       active = true;
       double acc[3] = {0., 0., 0.};
       for (uint32_t col = 0; col < r.len; ++col) {

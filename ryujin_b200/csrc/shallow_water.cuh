@@ -35,6 +35,7 @@ namespace rjb
     static constexpr bool aeos = false;
     static constexpr bool have_source_terms = true;
     static constexpr bool have_high_order_flux = true;
+    static constexpr bool edge_cache = false;
     using Params = ShallowWaterParams;
 
     struct Flux {

@@ -157,6 +157,8 @@ inline double __longlong_as_double(long long u) { double x; std::memcpy(&x, &u, 
 template <typename T> inline T __ldg(const T *p) { return *p; }
 inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { const auto old = *p; if (v < old) *p = v; return old; }
 inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { const auto old = *p; if (v > old) *p = v; return old; }
+inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { const unsigned int old = *p; *p = old + v; return old; }
+inline void __threadfence() {}
 inline int atomicOr(int *p, int v) { const int old = *p; *p = old | v; return old; }
 
 /* ---- block execution engine (host_emulation.cc) ---- */
@@ -196,3 +198,20 @@ template <typename F> struct rj_emu_call : rj_emu_thunk {
     });                                                                                                      \
   } while (0)
 #define RJ_LAUNCH_KERNEL(kernel, grid, block, stream, ...) RJ_LAUNCH_KERNEL_SMEM(kernel, grid, block, 0, stream, __VA_ARGS__)
+/* cooperative launches (kernels_fused.cuh) run as ONE block here: the blocks of a grid run one after the
+ * other in this engine, so a grid-wide barrier is only meaningful for a grid of one; the kernel's loops
+ * over virtual blocks cover the whole mesh with any grid size */
+#define RJ_LAUNCH_KERNEL_COOPERATIVE(kernel, grid, block, stream, arg) RJ_LAUNCH_KERNEL(kernel, ((void)(grid), 1), block, stream, arg)
+#define RJ_SPIN_YIELD() ::rjb::tile::emu_yield()
+namespace rjb
+{
+  namespace tile
+  {
+    void emu_yield();
+  }
+  template <typename Kernel>
+  inline int rj_cooperative_grid_limit(Kernel, int, int)
+  {
+    return 1;
+  }
+} // namespace rjb

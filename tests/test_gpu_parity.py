@@ -646,3 +646,42 @@ def test_streaming_transfers_match_the_blocking_ones():
         state.upload_begin(in_ptr[1])
     state.upload_end()
     module.synchronize()
+
+
+@pytest.mark.parametrize("setup", ["euler sod2d erk33", "euler vortex3d ssprk33", "euler sod2d erk54 iterations1",
+                                   "euler_aeos sod2d erk33", "shallow_water dam erk33"])
+def test_fused_update_kernel_is_bit_identical(setup, monkeypatch):
+    """kernels_fused.cuh: on small single-rank meshes a device-resident cycle runs prepare + step of
+    every substep as ONE persistent kernel with grid-wide barriers (RYUJIN_B200_FUSED=1; automatic
+    below 262144 rows).  Same bodies, same order: state, tau sequence and counters must be the bits of
+    the separate kernels (RYUJIN_B200_FUSED=0), with a fraction of the launches."""
+    import ryujin_b200 as rj
+    from helpers import make_sw_product
+
+    words = setup.split()
+    equation, case, scheme = words[0], words[1], words[2]
+    params = {"limiter_iterations": 1} if "iterations1" in words else None
+    results = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("RYUJIN_B200_FUSED", fused)
+        if equation == "shallow_water":
+            od, module = make_sw_product("sw_dam2d_friction", [24, 20])
+        else:
+            od, module = make_product(case, [40, 12] if case == "sod2d" else [10, 8, 6], equation=equation, module_params=params)
+        ti = rj.TimeIntegrator(module, _scheme(scheme[:-2] + " " + scheme[-2:]), 0.3, 2.5, rj.CFLRecoveryStrategy.bang_bang_control)
+        state = module.state_vector()
+        state.interpolate(0.0)
+        launches0 = module.kernel_launches()
+        t, taus = 0.0, []
+        for _ in range(10):
+            tau = ti.step(state, t)
+            taus.append(tau)
+            t += tau
+        results[fused] = (state.download(), np.array(taus), module.n_restarts(), module.n_warnings(),
+                          module.kernel_launches() - launches0)
+    U0, taus0, nr0, nw0, launches_separate = results["0"]
+    U1, taus1, nr1, nw1, launches_fused = results["1"]
+    assert np.array_equal(U1, U0) and np.array_equal(taus1, taus0) and (nr1, nw1) == (nr0, nw0)
+    # erk 54: the substeps with 3 and 4 stage states take the separate kernels (RJ_FUSED_MAX_STAGES = 2)
+    factor = 1 if "erk54" in words else 3
+    assert launches_fused * factor < launches_separate, (launches_fused, launches_separate)

@@ -33,4 +33,4 @@ echo "$VARIANTS" | while IFS= read -r line; do
   echo "built $name ($flags)"
 done
 rm -f build/vcl_fma/module.o
-make -s   # restore the default object and library
+make -s -j2   # restore the default object and library
