@@ -72,24 +72,22 @@
 #ifndef RJ_DIJ_W
 #define RJ_DIJ_W 4 /* warps per slice of the edge-parallel d_ij kernel */
 #endif
-/* Edge cache: quantities of the sweep that are symmetric in (i, j) are evaluated once per edge by the
- * edge-parallel kernel of step 2 (which already holds U_i and U_j and already mirrors d_ij) instead of
- * twice by the row-parallel step 4.  For the polytropic Euler limiter that is the specific entropy of
- * the midpoint state (one pow + one division per stencil entry, limiter.h:314-319): (U_i + U_j) * .5 is
- * the same state in row i and in row j bit for bit, so are the cached values.
- *   0: off (step 4 evaluates it per entry)   1: inside k_dij   2: the same kernel body, launched on its own
- *   3: inside k_alpha (row parallel, entries j > i, mirrored) */
+/* Edge cache: a quantity of step 4 that is symmetric in (i, j) is evaluated once per edge instead of twice.
+ * For the polytropic Euler limiter that is the specific entropy of the midpoint state (one pow + one division
+ * per stencil entry, limiter.h:314-319): (U_i + U_j) * .5 is the same state in row i and in row j bit for
+ * bit, so are the cached values.  k_alpha evaluates it for the entries j > i (it has U_j gathered and is bound
+ * by gather latency, not by FP64 issue) and mirrors it into (j, i) as k_dij mirrors d_ij; step 4 reads it.
+ * Measured on the B200 (profiles/r2h, r2i): step 4 -1.4 ms, k_alpha +1.1 ms per update of 8M DoFs; doing it
+ * in k_dij instead (edge parallel, FP64-issue bound already) gave +1.2 ms there: removed.
+ *   0: off (step 4 evaluates the entropy per entry)   1: on */
 #ifndef RJ_EDGE_CACHE
 #define RJ_EDGE_CACHE 0
 #endif
-#ifndef RJ_MB_EC
-#define RJ_MB_EC 8
-#endif
-#ifndef RJ_DIJ_RELOAD
-#define RJ_DIJ_RELOAD 0
-#endif
 #ifndef RJ_MB_ALPHA
 #define RJ_MB_ALPHA 8
+#endif
+#ifndef RJ_MB_ALPHA_CACHE
+#define RJ_MB_ALPHA_CACHE 6 /* with the edge cache (one pow per entry j > i): 8 -> 3.56 ms, 6 -> 3.69, 5 -> 4.69 next to step 4 at 6.42 / 6.29 / 6.19 */
 #endif
 #ifndef RJ_MB_LOW
 #define RJ_MB_LOW 4
@@ -126,6 +124,9 @@ namespace rjb
     double tau;                      /* time step used by the update kernels */
     int restart_needed;
     int numeric_error;
+    /* last-block-done counters of the kernels that carry the scalar work of a substep (k_dii_tau_final,
+     * k_high_order_record); zero between launches */
+    unsigned int blocks_done_tau, blocks_done_step;
   };
 
   /* device scalars of one TimeIntegrator cycle (device-resident stepping: the substeps of a
@@ -382,7 +383,7 @@ namespace rjb
    *  k_alpha ROW parallel: the entropy-viscosity commutator, accumulated in
    *          column order in one thread as the reference does.
    * ---------------------------------------------------------------------- */
-  template <class Eq, int W, bool do_dij, bool do_cache>
+  template <class Eq, int W>
   RJ_DEVICE void dij_body(const uint32_t vblock,
                           StencilView v,
                           typename Eq::Params prm,
@@ -390,8 +391,7 @@ namespace rjb
                           uint32_t slice_end,
                           const double *__restrict__ U,
                           const double *__restrict__ prec,
-                          double *__restrict__ dij,
-                          double *__restrict__ edge_cache)
+                          double *__restrict__ dij)
   {
     constexpr int k = Eq::k, dim = Eq::dim, np = Eq::n_prec;
     const uint32_t g = slice_begin + vblock;
@@ -406,77 +406,47 @@ namespace rjb
       return;
     const uint32_t base = v.slice_offsets[g] + lane;
 
-#if !RJ_DIJ_RELOAD
     double U_i[k], prec_i[np];
     load_state<k>(U, v.ld, i, U_i);
     load_state<np>(prec, v.ld, i, prec_i);
-#endif
 
     for (uint32_t col = w; col < len; col += W) {
-      if (col == 0) {
-        if constexpr (do_cache) {
-          double prec_d[np];
-          load_state<np>(prec, v.ld, i, prec_d);
-          edge_cache[base] = Eq::edge_value_diagonal(prec_d);
-        }
+      if (col == 0)
         continue;
-      }
       const uint32_t e = base + col * 32;
       const uint32_t j = v.cols[e];
       if (j < i)
         continue;
-#if RJ_DIJ_RELOAD
-      /* experiment: the row's own state is re-read per solve (volatile: not hoisted) instead of being
-       * kept in registers across the Riemann solves */
-      double U_i[k], prec_i[np];
-#pragma unroll
-      for (int q = 0; q < k; ++q)
-        U_i[q] = *(const volatile double *)&U[size_t(q) * v.ld + i];
-#pragma unroll
-      for (int q = 0; q < np; ++q)
-        prec_i[q] = *(const volatile double *)&prec[size_t(q) * v.ld + i];
-#endif
-      double U_j[k], prec_j[np];
+      double U_j[k], prec_j[np], c_ij[dim];
       load_state<k>(U, v.ld, j, U_j);
       load_state<np>(prec, v.ld, j, prec_j);
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
+
+      double nrm2 = c_ij[0] * c_ij[0];
+#pragma unroll
+      for (int d = 1; d < dim; ++d)
+        nrm2 += c_ij[d] * c_ij[d];
+      const double nrm = sqrt(nrm2);
+      const double inv = 1. / nrm;
+      double n_ij[dim];
+#pragma unroll
+      for (int d = 0; d < dim; ++d)
+        n_ij[d] = c_ij[d] * inv;
+      const double lambda_max = Eq::riemann_lambda_max(prm, U_i, prec_i, U_j, prec_j, n_ij);
+      const double d_ij = nrm * lambda_max;
+      dij[e] = d_ij;
       const uint32_t eT = v.transposed[e];
-
-      if constexpr (do_cache) {
-        const double value = Eq::edge_value(prm, U_i, U_j);
-        edge_cache[e] = value;
-        if (eT < v.E_owned)
-          edge_cache[eT] = value;
-      }
-
-      if constexpr (do_dij) {
-        double c_ij[dim];
-#pragma unroll
-        for (int d = 0; d < dim; ++d)
-          c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
-
-        double nrm2 = c_ij[0] * c_ij[0];
-#pragma unroll
-        for (int d = 1; d < dim; ++d)
-          nrm2 += c_ij[d] * c_ij[d];
-        const double nrm = sqrt(nrm2);
-        const double inv = 1. / nrm;
-        double n_ij[dim];
-#pragma unroll
-        for (int d = 0; d < dim; ++d)
-          n_ij[d] = c_ij[d] * inv;
-        const double lambda_max = Eq::riemann_lambda_max(prm, U_i, prec_i, U_j, prec_j, n_ij);
-        const double d_ij = nrm * lambda_max;
-        dij[e] = d_ij;
-        if (eT < v.E_owned)
-          dij[eT] = d_ij;
-      }
+      if (eT < v.E_owned)
+        dij[eT] = d_ij;
     }
   }
 
-  template <class Eq, int W, bool do_dij = true, bool do_cache = false>
-  __global__ void __launch_bounds__(32 * W, do_dij ? RJ_MB_DIJ : RJ_MB_EC) k_dij(StencilView v, typename Eq::Params prm, uint32_t slice_begin, uint32_t slice_end, const double *__restrict__ U, const double *__restrict__ prec, double *__restrict__ dij, double *__restrict__ edge_cache)
+  template <class Eq, int W>
+  __global__ void __launch_bounds__(32 * W, RJ_MB_DIJ) k_dij(StencilView v, typename Eq::Params prm, uint32_t slice_begin, uint32_t slice_end, const double *__restrict__ U, const double *__restrict__ prec, double *__restrict__ dij)
   {
-    dij_body<Eq, W, do_dij, do_cache>(blockIdx.x, v, prm, slice_begin, slice_end, U, prec, dij, edge_cache);
+    dij_body<Eq, W>(blockIdx.x, v, prm, slice_begin, slice_end, U, prec, dij);
   }
 
   template <class Eq, bool do_cache>
@@ -518,8 +488,7 @@ namespace rjb
         c_ij[d] = v.cij[size_t(d) * v.E_owned + e];
       indicator.accumulate(prm, U_i, prec_i, U_j, prec_j, Eq::load_aux(aux_j), c_ij);
       if constexpr (do_cache) {
-        /* RJ_EDGE_CACHE == 3: the symmetric edge quantity of step 4 is evaluated here, in the shadow of
-         * the gather latency this sweep is bound by, for j > i, and mirrored (as k_dij mirrors d_ij) */
+        /* the symmetric edge quantity of step 4, for j > i, mirrored (as k_dij mirrors d_ij) */
         if (col == 0)
           edge_cache[e] = Eq::edge_value_diagonal(prec_i);
         else if (j > i) {
@@ -537,11 +506,23 @@ namespace rjb
   }
 
   template <class Eq, bool do_cache = false>
-  __global__ void __launch_bounds__(128, RJ_MB_ALPHA) k_alpha(StencilView v, typename Eq::Params prm, uint32_t row_begin, uint32_t row_end, const double *__restrict__ U, const double *__restrict__ prec, const double *__restrict__ aux, double *__restrict__ alpha, double *__restrict__ edge_cache)
+  __global__ void __launch_bounds__(128, do_cache ? RJ_MB_ALPHA_CACHE : RJ_MB_ALPHA) k_alpha(StencilView v, typename Eq::Params prm, uint32_t row_begin, uint32_t row_end, const double *__restrict__ U, const double *__restrict__ prec, const double *__restrict__ aux, double *__restrict__ alpha, double *__restrict__ edge_cache)
   {
     alpha_body<Eq, do_cache>(blockIdx.x, v, prm, row_begin, row_end, U, prec, aux, alpha, edge_cache);
   }
 
+
+  /* Small single-rank meshes: d_ij and alpha_i (both read the prepared state only) as ONE launch of
+   * heterogeneous blocks -- blocks [0, n_slices) run the edge-parallel d_ij body, the rest the row-parallel
+   * indicator -- one dependency latency less per update where launches, not bandwidth, bound the update. */
+  template <class Eq, bool alpha_cache>
+  __global__ void __launch_bounds__(128, RJ_MB_ALPHA) k_dij_alpha(StencilView v, typename Eq::Params prm, uint32_t n_slices, const double *__restrict__ U, const double *__restrict__ prec, const double *__restrict__ aux, double *__restrict__ dij, double *__restrict__ alpha, double *__restrict__ edge_cache)
+  {
+    if (blockIdx.x < n_slices)
+      dij_body<Eq, 4>(blockIdx.x, v, prm, 0u, n_slices, U, prec, dij);
+    else
+      alpha_body<Eq, alpha_cache>(blockIdx.x - n_slices, v, prm, 0u, v.n_owned, U, prec, aux, alpha, edge_cache);
+  }
 
   /* Step 3a: complete d_ij on coupling boundary pairs (i < j),
    * hyperbolic_module.template.h:461-490. */
@@ -659,6 +640,8 @@ namespace rjb
     s->tau = 0.;
     s->restart_needed = 0;
     s->numeric_error = 0;
+    s->blocks_done_tau = 0;
+    s->blocks_done_step = 0;
   }
 
   /* Where a substep takes tau and tau_max from: host values (the reference API), or the
@@ -701,6 +684,48 @@ namespace rjb
   {
     cycle->restart[substep] = s->restart_needed;
     cycle->numeric_error[substep] = s->numeric_error;
+  }
+
+  /* Single-rank device-resident cycles: the scalar kernels of a substep (k_reset_scalars, k_tau_local,
+   * k_tau_finalize, k_cycle_record: 4 of 14 launches, each a few microseconds of dependency latency) are
+   * folded into the sweeps around them.  The block that finishes LAST (fence + atomic counter) does the
+   * scalar work: it sees what every other block wrote before its own fence.  The scalars are left clean
+   * for the next substep, which is what k_reset_scalars would have done. */
+  RJ_DEVICE bool last_block_done(unsigned int *counter)
+  {
+    /* one thread per block calls this after the block's results are written (and fenced) */
+    __threadfence();
+    const bool last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    if (last) {
+      *counter = 0;
+      __threadfence();
+    }
+    return last;
+  }
+
+  /* k_dii_tau, then (last block) k_tau_local + k_tau_finalize; re-arms tau_max_bits */
+  __global__ void k_dii_tau_final(StencilView v, uint32_t row_begin, uint32_t row_end, double cfl, double *__restrict__ dij, StepScalars *scalars, TauSource src, CycleScalars *cycle)
+  {
+    dii_tau_body(blockIdx.x, v, row_begin, row_end, cfl, dij, scalars);
+    /* the block's atomicMin was issued by thread 0 (lane 0 of warp 0) */
+    if (threadIdx.x == 0 && last_block_done(&scalars->blocks_done_tau)) {
+      StepScalars *s = scalars;
+      const double local = __longlong_as_double((long long)*(volatile unsigned long long *)&s->tau_max_bits);
+      double tau_max_in = src.tau_max;
+      if (src.mode == 1)
+        tau_max_in = cycle->tau_max == DBL_MAX ? DBL_MAX : __ddiv_rn(cycle->tau_max, src.divisor);
+      else if (src.mode == 2)
+        tau_max_in = DBL_MAX;
+      const double tau_max = fmin(local, tau_max_in);
+      s->tau_max = tau_max;
+      if (isnan(tau_max) || isinf(tau_max) || !(tau_max > 0.))
+        s->numeric_error = 1;
+      const double tau_in = src.mode == 0 ? src.tau : (src.mode == 1 ? 0. : cycle->tau);
+      s->tau = (tau_in == 0. ? tau_max : tau_in);
+      if (src.mode == 1)
+        cycle->tau = s->tau;
+      s->tau_max_bits = (unsigned long long)__double_as_longlong(DBL_MAX);
+    }
   }
 
 
@@ -1119,6 +1144,20 @@ namespace rjb
   __global__ void __launch_bounds__(128, RJ_MB_HO) k_high_order(StencilView v, typename Eq::Params prm, uint32_t row_begin, uint32_t row_end, const double *__restrict__ bounds, const double *__restrict__ pij, const double *__restrict__ lij, double *__restrict__ lij_next, double *__restrict__ U_new)
   {
     high_order_body<Eq, last_round>(blockIdx.x, v, prm, row_begin, row_end, bounds, pij, lij, lij_next, U_new);
+  }
+
+  /* the final high-order update, then (last block) k_cycle_record; clears the substep's flags */
+  template <class Eq>
+  __global__ void __launch_bounds__(128, RJ_MB_HO) k_high_order_record(StencilView v, typename Eq::Params prm, uint32_t row_begin, uint32_t row_end, const double *__restrict__ bounds, const double *__restrict__ pij, const double *__restrict__ lij, double *__restrict__ lij_next, double *__restrict__ U_new, StepScalars *scalars, CycleScalars *cycle, int substep)
+  {
+    high_order_body<Eq, true>(blockIdx.x, v, prm, row_begin, row_end, bounds, pij, lij, lij_next, U_new);
+    __syncthreads();
+    if (threadIdx.x == 0 && last_block_done(&scalars->blocks_done_step)) {
+      cycle->restart[substep] = *(volatile int *)&scalars->restart_needed;
+      cycle->numeric_error[substep] = *(volatile int *)&scalars->numeric_error;
+      scalars->restart_needed = 0;
+      scalars->numeric_error = 0;
+    }
   }
 
 

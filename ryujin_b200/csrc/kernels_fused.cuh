@@ -38,6 +38,13 @@
 #define RJ_MB_FUSED 4 /* resident blocks of 128 threads per SM: 128 registers, as the heaviest phase (step 4) */
 #endif
 
+#if defined(__CUDA_ARCH__)
+/* fence.acq_rel.gpu instead of __threadfence() (= fence.sc.gpu): the barrier needs release / acquire only */
+#define RJ_FENCE_GPU() asm volatile("fence.acq_rel.gpu;" ::: "memory")
+#else
+#define RJ_FENCE_GPU() __threadfence()
+#endif
+
 namespace rjb
 {
   /* Grid-wide barrier of a cooperative launch: one arrival counter that only grows during a launch
@@ -54,11 +61,11 @@ namespace rjb
     __syncthreads();
     if (threadIdx.x == 0) {
       epoch += gridDim.x;
-      __threadfence();
+      RJ_FENCE_GPU(); /* release: this block's writes (ordered before by the __syncthreads above) */
       atomicAdd(&barrier->count, 1u);
       while (*(volatile unsigned int *)&barrier->count < epoch)
         RJ_SPIN_YIELD();
-      __threadfence();
+      RJ_FENCE_GPU(); /* acquire: invalidates this SM's L1 (CCTL.IVALL) */
     }
     __syncthreads();
   }
@@ -116,6 +123,8 @@ namespace rjb
       s->tau = 0.;
       s->restart_needed = 0;
       s->numeric_error = 0;
+      s->blocks_done_tau = 0;
+      s->blocks_done_step = 0;
     }
     if (a.do_prepare) {
       RJ_FOR_VBLOCKS(vb, (a.n_bgroups + B - 1) / B)
@@ -136,9 +145,9 @@ namespace rjb
 
     /* phase 2 */
     RJ_FOR_VBLOCKS(vb, a.n_slices)
-      dij_body<Eq, 4, true, cache && RJ_EDGE_CACHE != 3>(vb, a.v, a.prm, 0u, a.n_slices, a.U, a.prec, a.dij, a.edge_cache);
+      dij_body<Eq, 4>(vb, a.v, a.prm, 0u, a.n_slices, a.U, a.prec, a.dij);
     RJ_FOR_VBLOCKS(vb, row_blocks)
-      alpha_body<Eq, cache && RJ_EDGE_CACHE == 3>(vb, a.v, a.prm, 0u, n_owned, a.U, a.prec, a.aux, a.alpha, a.edge_cache);
+      alpha_body<Eq, cache>(vb, a.v, a.prm, 0u, n_owned, a.U, a.prec, a.aux, a.alpha, a.edge_cache);
     grid_sync(a.barrier, epoch);
 
     /* phase 3 */
@@ -226,6 +235,10 @@ namespace rjb
           a.cycle->restart[a.substep] = *(volatile int *)&a.scalars->restart_needed;
           a.cycle->numeric_error[a.substep] = *(volatile int *)&a.scalars->numeric_error;
         }
+        /* leave the scalars clean, as the folded scalar kernels of the separate path expect them */
+        a.scalars->restart_needed = 0;
+        a.scalars->numeric_error = 0;
+        a.scalars->tau_max_bits = (unsigned long long)__double_as_longlong(DBL_MAX);
         a.barrier->count = 0;
         a.barrier->finished = 0;
       }

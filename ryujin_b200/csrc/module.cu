@@ -123,9 +123,12 @@ struct rj_hyperbolic_module {
   /* scratch, hyperbolic_module.h:319-333 */
   double *alpha = nullptr, *bounds = nullptr, *r = nullptr;
   double *dij = nullptr, *lij = nullptr, *lij_next = nullptr, *pij = nullptr;
-  /* one persistent kernel per update on small single-rank meshes (kernels_fused.cuh).  fused_mode: 0 never,
-   * 1 always (single rank), -1 automatic: meshes of at most fused_max_rows rows; RYUJIN_B200_FUSED */
-  int fused_mode = -1;
+  bool fold_scalar_kernels = true; /* RYUJIN_B200_FOLD=0: the separate scalar kernels (A/B, bit-identical) */
+  uint32_t small_mesh_rows = 262144; /* at most: d_ij and alpha_i as one launch (k_dij_alpha); RYUJIN_B200_SMALL_MESH_ROWS */
+  /* one persistent kernel per update on single-rank meshes (kernels_fused.cuh).  fused_mode: 0 never (default:
+   * measured slower than graph replay of the separate kernels at every mesh size, profiles/r2i_small_mesh.txt),
+   * 1 always, -1: meshes of at most fused_max_rows rows; RYUJIN_B200_FUSED */
+  int fused_mode = 0;
   uint32_t fused_max_rows = RJ_FUSED_MAX_ROWS_DEFAULT;
   GridBarrier *fused_barrier = nullptr;
   int fused_grid_limit[5] = {0, 0, 0, 0, 0}; /* co-resident blocks of k_update_fused<Eq, stages>, queried once */
@@ -189,6 +192,7 @@ struct rj_hyperbolic_module {
     TauSource src{0, tau, tau_max, 1.};
     enqueue_step(old_state, stages, stage_states, stage_weights, new_state, src, nullptr, 0);
     RJ_CUDA(cudaMemcpyAsync(h_scalars, scalars, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
+    launch(k_reset_scalars, 1, 1, scalars); /* device-resident cycles rely on clean scalars between substeps */
     RJ_CUDA(cudaStreamSynchronize(stream));
     if (profiling)
       collect_profile();
@@ -250,6 +254,9 @@ struct rj_hyperbolic_module {
     if (want_edge_cache)
       alloc(edge_cache, od->E_owned);
     RJ_CUDA(cudaMalloc(&scalars, sizeof(StepScalars)));
+    cur = stream;
+    launch(k_reset_scalars, 1, 1, scalars);
+    launches = 0;
     RJ_CUDA(cudaMalloc(&fused_barrier, sizeof(GridBarrier)));
     RJ_CUDA(cudaMemsetAsync(fused_barrier, 0, sizeof(GridBarrier), stream));
     RJ_CUDA(cudaMallocHost(&h_scalars, sizeof(StepScalars)));
@@ -958,25 +965,29 @@ namespace rjb
         }
       };
 
+      /* single-rank device-resident cycle: the scalar kernels are folded into the sweeps (kernels.cuh:
+       * k_dii_tau_final, k_high_order_record); the scalars are clean on entry */
+      const bool folded = fold_scalar_kernels && !multi && cycle != nullptr && mp.limiter_iterations != 0;
       tag(P_OTHER);
-      launch(k_reset_scalars, 1, 1, scalars);
+      if (!folded)
+        launch(k_reset_scalars, 1, 1, scalars);
 
       /* Step 2: d_ij (j > i), alpha_i; then C3 */
       tag(P_DIJ);
-      {
+      const bool merged_step2 = folded && !profiling && n_owned <= small_mesh_rows;
+      if (merged_step2) {
+        launch(k_dij_alpha<Eq, use_edge_cache>, (size_t(od->n_slices) + (n_owned + 127) / 128) * 128, 128, v, prm, od->n_slices,
+               old_state.U, old_state.prec, old_state.aux, dij, alpha, edge_cache);
+      } else {
         constexpr int W = RJ_DIJ_W; /* warps per slice in the edge-parallel d_ij kernel */
-        constexpr bool fused = use_edge_cache && RJ_EDGE_CACHE == 1;
-        launch(k_dij<Eq, W, true, fused>, size_t(od->n_slices) * 32 * W, 32 * W, v, prm, 0u, od->n_slices, old_state.U,
-               old_state.prec, dij, edge_cache);
-        if constexpr (use_edge_cache && RJ_EDGE_CACHE == 2)
-          launch(k_dij<Eq, W, false, true>, size_t(od->n_slices) * 32 * W, 32 * W, v, prm, 0u, od->n_slices, old_state.U,
-                 old_state.prec, dij, edge_cache);
+        launch(k_dij<Eq, W>, size_t(od->n_slices) * 32 * W, 32 * W, v, prm, 0u, od->n_slices, old_state.U, old_state.prec, dij);
       }
       sweep(
           [&](uint32_t b, uint32_t e) {
             tag(P_ALPHA);
-            launch_rows(k_alpha<Eq, use_edge_cache && RJ_EDGE_CACHE == 3>, b, e, v, prm, b, e, old_state.U, old_state.prec,
-                        old_state.aux, alpha, edge_cache);
+            if (!merged_step2)
+              launch_rows(k_alpha<Eq, use_edge_cache>, b, e, v, prm, b, e, old_state.U, old_state.prec,
+                          old_state.aux, alpha, edge_cache);
             if (e == n_owned && (b < e || b == 0)) {
               /* Step 3: boundary d_ij, d_ii, tau_max (need d_ij only) */
               tag(P_BOUNDARY_DIJ);
@@ -996,9 +1007,13 @@ namespace rjb
                      old_state.prec,
                      dij);
               tag(P_DII_TAU);
-              launch_rows(k_dii_tau, 0, n_owned, v, 0u, n_owned, cfl, dij, scalars);
-              tag(P_OTHER);
-              launch(k_tau_local, 1, 1, scalars, tau_source, (const CycleScalars *)cycle);
+              if (folded)
+                launch_rows(k_dii_tau_final, 0, n_owned, v, 0u, n_owned, cfl, dij, scalars, tau_source, cycle);
+              else {
+                launch_rows(k_dii_tau, 0, n_owned, v, 0u, n_owned, cfl, dij, scalars);
+                tag(P_OTHER);
+                launch(k_tau_local, 1, 1, scalars, tau_source, (const CycleScalars *)cycle);
+              }
             }
           },
           [&] { exchange_vector(alpha, 1); });
@@ -1013,7 +1028,8 @@ namespace rjb
         if (ov)
           join_comm();
       }
-      launch(k_tau_finalize, 1, 1, scalars, tau_source, cycle);
+      if (!folded)
+        launch(k_tau_finalize, 1, 1, scalars, tau_source, cycle);
 
       auto low_order_rows = [&](uint32_t b, uint32_t e) {
         tag(P_LOW_ORDER);
@@ -1052,7 +1068,11 @@ namespace rjb
           std::swap(lij, lij_next);
         if (last_round) {
           tag(P_HIGH_ORDER_FINAL);
-          launch_rows(k_high_order<Eq, true>, 0, n_owned, v, prm, 0u, n_owned, bounds, pij, lij, lij_next, new_state.U);
+          if (folded)
+            launch_rows(k_high_order_record<Eq>, 0, n_owned, v, prm, 0u, n_owned, bounds, pij, lij, lij_next, new_state.U,
+                        scalars, cycle, substep);
+          else
+            launch_rows(k_high_order<Eq, true>, 0, n_owned, v, prm, 0u, n_owned, bounds, pij, lij, lij_next, new_state.U);
         } else
           sweep(
               [&](uint32_t b, uint32_t e) {
@@ -1081,7 +1101,7 @@ namespace rjb
         if (ov)
           join_comm();
       }
-      if (cycle)
+      if (cycle && !folded)
         launch(k_cycle_record, 1, 1, (const StepScalars *)scalars, cycle, substep);
     }
   };
@@ -1357,7 +1377,7 @@ namespace rjb
       }
       key.push_back(reinterpret_cast<const void *>(
           uintptr_t((hm.overlapping() ? unsigned(hm.overlap_mode) : 0u) | (unsigned(hm.tile_mask) << 2) |
-                    (hm.fused_eligible() ? 1u << 8 : 0u))));
+                    (hm.fused_eligible() ? 1u << 8 : 0u) | (hm.fold_scalar_kernels ? 1u << 9 : 0u))));
       uint64_t cfl_bits;
       std::memcpy(&cfl_bits, &hm.cfl, sizeof(cfl_bits));
       key.push_back(reinterpret_cast<const void *>(cfl_bits));
@@ -1813,6 +1833,10 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
       RJ_CUDA(cudaEventCreateWithFlags(&hm->ev_fork, cudaEventDisableTiming));
       RJ_CUDA(cudaEventCreateWithFlags(&hm->ev_join, cudaEventDisableTiming));
     }
+    if (const char *env = std::getenv("RYUJIN_B200_SMALL_MESH_ROWS"))
+      hm->small_mesh_rows = uint32_t(std::min<long>(std::max<long>(std::atol(env), 0), 0x7fffffffL));
+    if (const char *env = std::getenv("RYUJIN_B200_FOLD"))
+      hm->fold_scalar_kernels = std::string(env) != "0";
     if (const char *env = std::getenv("RYUJIN_B200_FUSED")) {
       /* 0: never; 1: every single-rank module; N > 1: meshes of at most N rows */
       const long value = std::atol(env);
