@@ -21,16 +21,6 @@
 #ifndef RJ_LAUNCH_KERNEL
 #define RJ_LAUNCH_KERNEL(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #define RJ_LAUNCH_KERNEL_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-/* cooperative launch (all blocks co-resident: grid-wide barriers inside the kernel) of a kernel with ONE
- * by-value argument; rj_cooperative_grid_limit = the number of blocks that can be resident at once */
-#define RJ_LAUNCH_KERNEL_COOPERATIVE(kernel, grid, block, stream, arg)                                                      \
-  do {                                                                                                                      \
-    void *rj_kernel_args[] = {const_cast<void *>(static_cast<const void *>(&(arg)))};                                       \
-    RJ_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kernel), dim3(grid), dim3(block), rj_kernel_args, 0, \
-                                        (stream)));                                                                         \
-  } while (0)
-#define RJ_SPIN_YIELD() ((void)0)
-#define RJ_REAL_DEVICE 1
 #endif
 
 /* Which pow() the equation modules call (every pow of the path goes through path_pow): the
@@ -108,20 +98,6 @@ namespace rjb
     p_1 = fmin(t_1, t_2);
     p_2 = fmax(t_1, t_2);
   }
-
-#ifdef RJ_REAL_DEVICE
-  template <typename Kernel>
-  inline int rj_cooperative_grid_limit(Kernel kernel, int block, int device)
-  {
-    int per_sm = 0, sms = 0, cooperative = 0;
-    if (cudaDeviceGetAttribute(&cooperative, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !cooperative)
-      throw std::runtime_error("cooperative kernel launches are not supported on this device");
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm * sms < 1)
-      throw std::runtime_error("occupancy query of the fused update kernel failed");
-    return per_sm * sms;
-  }
-#endif
 
   /* host side error plumbing */
   struct CudaError : std::runtime_error {

@@ -81,7 +81,7 @@
  * in k_dij instead (edge parallel, FP64-issue bound already) gave +1.2 ms there: removed.
  *   0: off (step 4 evaluates the entropy per entry)   1: on */
 #ifndef RJ_EDGE_CACHE
-#define RJ_EDGE_CACHE 0
+#define RJ_EDGE_CACHE 1
 #endif
 #ifndef RJ_MB_ALPHA
 #define RJ_MB_ALPHA 8
@@ -217,8 +217,8 @@ namespace rjb
                                                 const double *__restrict__ bposition,
                                                 const int32_t *__restrict__ bid,
                                                 uint32_t ld,
-                                                typename Eq::Params prm,
-                                                IV iv,
+                                                const typename Eq::Params &prm,
+                                                const IV &iv,
                                                 double t_host,
                                                 const CycleScalars *__restrict__ cycle,
                                                 double tau_factor,
@@ -287,8 +287,8 @@ namespace rjb
    * ---------------------------------------------------------------------- */
   template <class Eq>
   RJ_DEVICE void precompute_body(const uint32_t vblock,
-                                 StencilView v,
-                                 typename Eq::Params prm,
+                                 const StencilView &v,
+                                 const typename Eq::Params &prm,
                                  uint32_t row_begin,
                                  uint32_t row_end,
                                  const double *__restrict__ U,
@@ -332,8 +332,8 @@ namespace rjb
    * component 0 of other rows, writes components 1.. of its own row: no hazard within the launch. */
   template <class Eq>
   RJ_DEVICE void precompute_stencil_body(const uint32_t vblock,
-                                         StencilView v,
-                                         typename Eq::Params prm,
+                                         const StencilView &v,
+                                         const typename Eq::Params &prm,
                                          uint32_t row_begin,
                                          uint32_t row_end,
                                          const double *__restrict__ U,
@@ -385,8 +385,8 @@ namespace rjb
    * ---------------------------------------------------------------------- */
   template <class Eq, int W>
   RJ_DEVICE void dij_body(const uint32_t vblock,
-                          StencilView v,
-                          typename Eq::Params prm,
+                          const StencilView &v,
+                          const typename Eq::Params &prm,
                           uint32_t slice_begin,
                           uint32_t slice_end,
                           const double *__restrict__ U,
@@ -451,8 +451,8 @@ namespace rjb
 
   template <class Eq, bool do_cache>
   RJ_DEVICE void alpha_body(const uint32_t vblock,
-                            StencilView v,
-                            typename Eq::Params prm,
+                            const StencilView &v,
+                            const typename Eq::Params &prm,
                             uint32_t row_begin,
                             uint32_t row_end,
                             const double *__restrict__ U,
@@ -536,7 +536,7 @@ namespace rjb
                                    const double *__restrict__ pair_cji,
                                    uint32_t ld,
                                    uint32_t E_owned,
-                                   typename Eq::Params prm,
+                                   const typename Eq::Params &prm,
                                    const double *__restrict__ U,
                                    const double *__restrict__ prec,
                                    double *__restrict__ dij)
@@ -584,7 +584,7 @@ namespace rjb
    * The row sum runs in column order in one thread; only the minimum over
    * rows (order independent) uses shuffles + one atomicMin per block. */
   RJ_DEVICE void dii_tau_body(const uint32_t vblock,
-                              StencilView v,
+                              const StencilView &v,
                               uint32_t row_begin,
                               uint32_t row_end,
                               double cfl,
@@ -738,14 +738,14 @@ namespace rjb
   template <class Eq, int stages>
   RJ_DEVICE void low_order_body(const uint32_t vblock,
                                 const double tau,
-                                StencilView v,
-                                typename Eq::Params prm,
+                                const StencilView &v,
+                                const typename Eq::Params &prm,
                                 uint32_t row_begin,
                                 uint32_t row_end,
                                 const double *__restrict__ U,
                                 const double *__restrict__ prec,
                                 const double *__restrict__ aux,
-                                StagePointers<stages> st,
+                                const StagePointers<stages> &st,
                                 const double *__restrict__ alpha,
                                 const double *__restrict__ dij,
                                 const double *__restrict__ edge_cache,
@@ -1013,8 +1013,8 @@ namespace rjb
   template <class Eq>
   RJ_DEVICE void pij_lij_body(const uint32_t vblock,
                               const double tau,
-                              StencilView v,
-                              typename Eq::Params prm,
+                              const StencilView &v,
+                              const typename Eq::Params &prm,
                               uint32_t row_begin,
                               uint32_t row_end,
                               const double *__restrict__ U_new,
@@ -1086,8 +1086,8 @@ namespace rjb
    * ---------------------------------------------------------------------- */
   template <class Eq, bool last_round>
   RJ_DEVICE void high_order_body(const uint32_t vblock,
-                                 StencilView v,
-                                 typename Eq::Params prm,
+                                 const StencilView &v,
+                                 const typename Eq::Params &prm,
                                  uint32_t row_begin,
                                  uint32_t row_end,
                                  const double *__restrict__ bounds,

@@ -11,7 +11,6 @@
 #include "initial_values.cuh"
 #include "kernels.cuh"
 #include "kernels_tile.cuh"
-#include "kernels_fused.cuh"
 #include "shallow_water.cuh"
 #include "euler_aeos.cuh"
 
@@ -125,33 +124,6 @@ struct rj_hyperbolic_module {
   double *dij = nullptr, *lij = nullptr, *lij_next = nullptr, *pij = nullptr;
   bool fold_scalar_kernels = true; /* RYUJIN_B200_FOLD=0: the separate scalar kernels (A/B, bit-identical) */
   uint32_t small_mesh_rows = 262144; /* at most: d_ij and alpha_i as one launch (k_dij_alpha); RYUJIN_B200_SMALL_MESH_ROWS */
-  /* one persistent kernel per update on single-rank meshes (kernels_fused.cuh).  fused_mode: 0 never (default:
-   * measured slower than graph replay of the separate kernels at every mesh size, profiles/r2i_small_mesh.txt),
-   * 1 always, -1: meshes of at most fused_max_rows rows; RYUJIN_B200_FUSED */
-  int fused_mode = 0;
-  uint32_t fused_max_rows = RJ_FUSED_MAX_ROWS_DEFAULT;
-  GridBarrier *fused_barrier = nullptr;
-  int fused_grid_limit[5] = {0, 0, 0, 0, 0}; /* co-resident blocks of k_update_fused<Eq, stages>, queried once */
-  bool fused_eligible() const
-  {
-    if (!RJ_FUSED || fused_mode == 0 || profiling || (comm && comm->n_ranks > 1))
-      return false;
-    return fused_mode == 1 || od->n_owned <= fused_max_rows;
-  }
-  /* prepare_state_vector(old) (if do_prepare) + step(old -> new) as one launch; false: not available */
-  virtual bool enqueue_prepare_step_fused(rj_state & /*old_state*/,
-                                          bool /*do_prepare*/,
-                                          double /*tau_factor*/,
-                                          int /*stages*/,
-                                          const rj_state *const * /*stage_states*/,
-                                          const double * /*stage_weights*/,
-                                          rj_state & /*new_state*/,
-                                          TauSource /*tau_source*/,
-                                          CycleScalars * /*cycle*/,
-                                          int /*substep*/)
-  {
-    return false;
-  }
   double *edge_cache = nullptr; /* E_owned doubles if the equation caches a symmetric edge quantity (RJ_EDGE_CACHE) */
   bool want_edge_cache = false;
   StepScalars *scalars = nullptr;
@@ -257,8 +229,6 @@ struct rj_hyperbolic_module {
     cur = stream;
     launch(k_reset_scalars, 1, 1, scalars);
     launches = 0;
-    RJ_CUDA(cudaMalloc(&fused_barrier, sizeof(GridBarrier)));
-    RJ_CUDA(cudaMemsetAsync(fused_barrier, 0, sizeof(GridBarrier), stream));
     RJ_CUDA(cudaMallocHost(&h_scalars, sizeof(StepScalars)));
     send_buffer_size =
         std::max<size_t>(size_t(od->n_send_rows) * std::max(k, std::max(n_prec, n_bounds)),
@@ -524,7 +494,6 @@ rj_hyperbolic_module::~rj_hyperbolic_module()
   f(pij);
   f(edge_cache);
   f(scalars);
-  f(fused_barrier);
   f(send_buffer);
   f(recv_buffer);
   f(staging);
@@ -796,117 +765,6 @@ namespace rjb
                     pij);
       };
         run(k_low_order<Eq, stages>, st);
-    }
-
-    /* kernels_fused.cuh: the whole update as one cooperative launch */
-    template <int stages>
-    void launch_fused(rj_state &old_state,
-                      bool do_prepare,
-                      double tau_factor,
-                      const rj_state *const *stage_states,
-                      const double *stage_weights,
-                      rj_state &new_state,
-                      TauSource tau_source,
-                      CycleScalars *cycle,
-                      int substep)
-    {
-      FusedUpdate<Eq, stages> a{};
-      a.v = view();
-      a.prm = prm;
-      a.iv = iv;
-      a.n_bgroups = od->n_bgroups;
-      a.bgroup_dof = od->bgroup_dof;
-      a.bgroup_start = od->bgroup_start;
-      a.bnormal = od->bnormal;
-      a.bposition = od->bposition;
-      a.bid = od->bid;
-      a.n_pairs = od->n_pairs;
-      a.pair_i = od->pair_i;
-      a.pair_j = od->pair_j;
-      a.pair_e = od->pair_e;
-      a.pair_eT = od->pair_eT;
-      a.pair_cji = od->pair_cji;
-      a.n_relevant = od->n_relevant;
-      a.n_slices = od->n_slices;
-      a.U = old_state.U;
-      a.prec = old_state.prec;
-      a.aux = old_state.aux;
-      a.initial_precomputed = initial_precomputed;
-      for (int s = 0; s < stages; ++s) {
-        a.st.U[s] = stage_states[s]->U;
-        a.st.prec[s] = stage_states[s]->prec;
-        a.st.aux[s] = stage_states[s]->aux;
-        a.st.weight[s] = stage_weights[s];
-      }
-      a.U_new = new_state.U;
-      a.alpha = alpha;
-      a.dij = dij;
-      a.edge_cache = edge_cache;
-      a.r = r;
-      a.bounds = bounds;
-      a.pij = pij;
-      a.lij = lij;
-      a.lij_next = lij_next;
-      a.scalars = scalars;
-      a.tau_source = tau_source;
-      a.cycle = cycle;
-      a.substep = substep;
-      a.tau_factor = tau_factor;
-      a.cfl = cfl;
-      a.n_iterations = mp.limiter_iterations;
-      a.do_prepare = do_prepare ? 1 : 0;
-      a.barrier = fused_barrier;
-      auto kernel = k_update_fused<Eq, stages>;
-      if (fused_grid_limit[stages] == 0)
-        fused_grid_limit[stages] = rj_cooperative_grid_limit(kernel, 128, od->device);
-      /* the d_ij phase has the most virtual blocks (one per slice) */
-      const unsigned int grid = std::max(1u, std::min<unsigned int>((unsigned int)fused_grid_limit[stages], od->n_slices));
-      RJ_LAUNCH_KERNEL_COOPERATIVE(kernel, grid, 128, cur, a);
-      RJ_CUDA(cudaGetLastError());
-      ++launches;
-      if (mp.limiter_iterations == 2)
-        std::swap(lij, lij_next); /* as enqueue_step leaves them */
-    }
-
-    bool enqueue_prepare_step_fused(rj_state &old_state,
-                                    bool do_prepare,
-                                    double tau_factor,
-                                    int stages,
-                                    const rj_state *const *stage_states,
-                                    const double *stage_weights,
-                                    rj_state &new_state,
-                                    TauSource tau_source,
-                                    CycleScalars *cycle,
-                                    int substep) override
-    {
-      /* instantiated for the schemes with at most RJ_FUSED_MAX_STAGES stage states (ERK 11/22/33, SSPRK);
-       * more stages take the separate kernels (every instantiation costs ~10 s of build time) */
-      if (!fused_eligible() || !cycle || stages > RJ_FUSED_MAX_STAGES)
-        return false;
-      RJ_CUDA(cudaSetDevice(od->device));
-      if (stages < 0)
-        throw InvalidArgument("rj_hyperbolic_module_step: stages must be in [0, 4]");
-      if (old_state.U == new_state.U)
-        throw InvalidArgument("rj_hyperbolic_module_step: old and new state must differ");
-      cur = stream;
-#if RJ_FUSED
-      switch (stages) {
-      case 0: launch_fused<0>(old_state, do_prepare, tau_factor, stage_states, stage_weights, new_state, tau_source, cycle, substep); break;
-#if RJ_FUSED_MAX_STAGES >= 1
-      case 1: launch_fused<1>(old_state, do_prepare, tau_factor, stage_states, stage_weights, new_state, tau_source, cycle, substep); break;
-#endif
-#if RJ_FUSED_MAX_STAGES >= 2
-      case 2: launch_fused<2>(old_state, do_prepare, tau_factor, stage_states, stage_weights, new_state, tau_source, cycle, substep); break;
-#endif
-#if RJ_FUSED_MAX_STAGES >= 3
-      case 3: launch_fused<3>(old_state, do_prepare, tau_factor, stage_states, stage_weights, new_state, tau_source, cycle, substep); break;
-#endif
-#if RJ_FUSED_MAX_STAGES >= 4
-      case 4: launch_fused<4>(old_state, do_prepare, tau_factor, stage_states, stage_weights, new_state, tau_source, cycle, substep); break;
-#endif
-      }
-#endif
-      return true;
     }
 
     /* hyperbolic_module.template.h:236-1211.
@@ -1303,27 +1161,9 @@ namespace rjb
     /* (t, tau_max) of this cycle: first 16 bytes of the pinned input block */
     RJ_CUDA(cudaMemcpyAsync(ti.d_cycle, &ti.h_cycle[0], 2 * sizeof(double), cudaMemcpyHostToDevice, hm.stream));
     int substep = 0;
-    const auto &program = ti.scheme.program;
-    for (size_t n = 0; n < program.size(); ++n) {
-      const Op &op = program[n];
+    for (const Op &op : ti.scheme.program) {
       switch (op.kind) {
-      case Op::PREPARE: {
-        /* small single-rank meshes: PREPARE(a) + STEP(a -> b) as ONE persistent kernel (kernels_fused.cuh) */
-        if (n + 1 < program.size() && program[n + 1].kind == Op::STEP && program[n + 1].a == op.a && hm.fused_eligible()) {
-          const Op &step = program[n + 1];
-          std::vector<const rj_state *> st;
-          for (int q : step.stages)
-            st.push_back(&ti.slot(sv, q));
-          TauSource src{step.divisor > 0. ? 1 : 2, 0., 0., step.divisor > 0. ? step.divisor : 1.};
-          if (hm.enqueue_prepare_step_fused(ti.slot(sv, op.a), true, op.c, int(st.size()), st.data(), step.weights.data(),
-                                            ti.slot(sv, step.b), src, ti.d_cycle, substep)) {
-            ++substep;
-            ++n; /* the STEP went with it */
-            break;
-          }
-        }
-        hm.prepare_state_vector(ti.slot(sv, op.a), 0., ti.d_cycle, op.c);
-      } break;
+      case Op::PREPARE: hm.prepare_state_vector(ti.slot(sv, op.a), 0., ti.d_cycle, op.c); break;
       case Op::SADD:
         if (rj_state_sadd(&ti.slot(sv, op.a), op.c, op.d, &ti.slot(sv, op.b)) != RJ_OK)
           throw CudaError(std::string("TimeIntegrator: sadd failed: ") + g_last_error);
@@ -1377,7 +1217,7 @@ namespace rjb
       }
       key.push_back(reinterpret_cast<const void *>(
           uintptr_t((hm.overlapping() ? unsigned(hm.overlap_mode) : 0u) | (unsigned(hm.tile_mask) << 2) |
-                    (hm.fused_eligible() ? 1u << 8 : 0u) | (hm.fold_scalar_kernels ? 1u << 9 : 0u))));
+                    (hm.fold_scalar_kernels ? 1u << 9 : 0u))));
       uint64_t cfl_bits;
       std::memcpy(&cfl_bits, &hm.cfl, sizeof(cfl_bits));
       key.push_back(reinterpret_cast<const void *>(cfl_bits));
@@ -1837,13 +1677,6 @@ int rj_hyperbolic_module_create(rj_hyperbolic_module **out,
       hm->small_mesh_rows = uint32_t(std::min<long>(std::max<long>(std::atol(env), 0), 0x7fffffffL));
     if (const char *env = std::getenv("RYUJIN_B200_FOLD"))
       hm->fold_scalar_kernels = std::string(env) != "0";
-    if (const char *env = std::getenv("RYUJIN_B200_FUSED")) {
-      /* 0: never; 1: every single-rank module; N > 1: meshes of at most N rows */
-      const long value = std::atol(env);
-      hm->fused_mode = value == 0 ? 0 : (value == 1 ? 1 : -1);
-      if (value > 1)
-        hm->fused_max_rows = uint32_t(std::min<long>(value, 0x7fffffffL));
-    }
     if (const char *env = std::getenv("RYUJIN_B200_OVERLAP")) {
       hm->overlap = std::string(env) != "0";
       if (hm->overlap)

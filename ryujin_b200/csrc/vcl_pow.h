@@ -47,10 +47,6 @@
 #define RJ_VCL_RINT(a) std::nearbyint(a)
 #endif
 
-#ifndef RJ_VCL_CONSTANT_MEMORY
-#define RJ_VCL_CONSTANT_MEMORY 0
-#endif
-
 namespace rjb
 {
   RJ_VCL_FN uint64_t vcl_bits(double x)
@@ -158,64 +154,41 @@ namespace rjb
     return z1;
   }
 
-  /* Constants of pow_template_d (vectormath_exp.h:1511-1553) and of the Taylor polynomial of its exponential.
-   * On sm_100a a double literal costs two UMOV at every use site (no 64-bit immediates, no constant-bank
-   * operands for FP64 instructions); from a __constant__ array two of them arrive per LDCU.128.  pow is
-   * inlined about ten times per sweep kernel.  Same values: the table is generated from the same list as the
-   * literals of the host path. */
-#define RJ_VCL_POW_CONSTANTS(X) \
-  X(ln2d_hi, 0.693145751953125) \
-  X(ln2d_lo, 1.42860682030941723212E-6) \
-  X(log2e, 1.44269504088896340736) /* VM_LOG2E */ \
-  X(ln2, 0.693147180559945309417) /* VM_LN2 */ \
-  X(sqrt2_half, 1.41421356237309504880 * 0.5) \
-  X(P0logl, 2.0039553499201281259648E1) \
-  X(P1logl, 5.7112963590585538103336E1) \
-  X(P2logl, 6.0949667980987787057556E1) \
-  X(P3logl, 2.9911919328553073277375E1) \
-  X(P4logl, 6.5787325942061044846969E0) \
-  X(P5logl, 4.9854102823193375972212E-1) \
-  X(P6logl, 4.5270000862445199635215E-5) \
-  X(Q0logl, 6.0118660497603843919306E1) \
-  X(Q1logl, 2.1642788614495947685003E2) \
-  X(Q2logl, 3.0909872225312059774938E2) \
-  X(Q3logl, 2.2176239823732856465394E2) \
-  X(Q4logl, 8.3047565967967209469434E1) \
-  X(Q5logl, 1.5062909083469192043167E1) \
-  X(p2, 1. / 2.) \
-  X(p3, 1. / 6.) \
-  X(p4, 1. / 24.) \
-  X(p5, 1. / 120.) \
-  X(p6, 1. / 720.) \
-  X(p7, 1. / 5040.) \
-  X(p8, 1. / 40320.) \
-  X(p9, 1. / 362880.) \
-  X(p10, 1. / 3628800.) \
-  X(p11, 1. / 39916800.) \
-  X(p12, 1. / 479001600.) \
-  X(p13, 1. / 6227020800.)
-
-#define RJ_VCL_INDEX(name, value) vcl_index_##name,
-  enum { RJ_VCL_POW_CONSTANTS(RJ_VCL_INDEX) vcl_n_constants };
-#undef RJ_VCL_INDEX
-#if defined(__CUDACC__) && RJ_VCL_CONSTANT_MEMORY
-#define RJ_VCL_VALUE(name, value) value,
-  static __constant__ double vcl_pow_constants[vcl_n_constants] = {RJ_VCL_POW_CONSTANTS(RJ_VCL_VALUE)};
-#undef RJ_VCL_VALUE
-#endif
-#if defined(__CUDA_ARCH__) && RJ_VCL_CONSTANT_MEMORY
-#define RJ_VCL_CONSTANT(name, value) vcl_pow_constants[vcl_index_##name]
-#else
-#define RJ_VCL_CONSTANT(name, value) (value)
-#endif
-
   template <bool fma>
   RJ_VCL_FN double vcl_pow(const double x0, const double y)
   {
-    /* the constants by name (RJ_VCL_POW_CONSTANTS); on the device they are read from constant memory */
-#define RJ_VCL_LOCAL(name, value) const double name = RJ_VCL_CONSTANT(name, value);
-    RJ_VCL_POW_CONSTANTS(RJ_VCL_LOCAL)
-#undef RJ_VCL_LOCAL
+    const double ln2d_hi = 0.693145751953125;
+    const double ln2d_lo = 1.42860682030941723212E-6;
+    const double log2e = 1.44269504088896340736; /* VM_LOG2E */
+    const double ln2 = 0.693147180559945309417;  /* VM_LN2 */
+    const double sqrt2_half = 1.41421356237309504880 * 0.5;
+
+    const double P0logl = 2.0039553499201281259648E1;
+    const double P1logl = 5.7112963590585538103336E1;
+    const double P2logl = 6.0949667980987787057556E1;
+    const double P3logl = 2.9911919328553073277375E1;
+    const double P4logl = 6.5787325942061044846969E0;
+    const double P5logl = 4.9854102823193375972212E-1;
+    const double P6logl = 4.5270000862445199635215E-5;
+    const double Q0logl = 6.0118660497603843919306E1;
+    const double Q1logl = 2.1642788614495947685003E2;
+    const double Q2logl = 3.0909872225312059774938E2;
+    const double Q3logl = 2.2176239823732856465394E2;
+    const double Q4logl = 8.3047565967967209469434E1;
+    const double Q5logl = 1.5062909083469192043167E1;
+
+    const double p2 = 1. / 2.;
+    const double p3 = 1. / 6.;
+    const double p4 = 1. / 24.;
+    const double p5 = 1. / 120.;
+    const double p6 = 1. / 720.;
+    const double p7 = 1. / 5040.;
+    const double p8 = 1. / 40320.;
+    const double p9 = 1. / 362880.;
+    const double p10 = 1. / 3628800.;
+    const double p11 = 1. / 39916800.;
+    const double p12 = 1. / 479001600.;
+    const double p13 = 1. / 6227020800.;
 
     const double x1 = fabs(x0);
     const uint64_t bx1 = vcl_bits(x1);

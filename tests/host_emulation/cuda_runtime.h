@@ -198,20 +198,3 @@ template <typename F> struct rj_emu_call : rj_emu_thunk {
     });                                                                                                      \
   } while (0)
 #define RJ_LAUNCH_KERNEL(kernel, grid, block, stream, ...) RJ_LAUNCH_KERNEL_SMEM(kernel, grid, block, 0, stream, __VA_ARGS__)
-/* cooperative launches (kernels_fused.cuh) run as ONE block here: the blocks of a grid run one after the
- * other in this engine, so a grid-wide barrier is only meaningful for a grid of one; the kernel's loops
- * over virtual blocks cover the whole mesh with any grid size */
-#define RJ_LAUNCH_KERNEL_COOPERATIVE(kernel, grid, block, stream, arg) RJ_LAUNCH_KERNEL(kernel, ((void)(grid), 1), block, stream, arg)
-#define RJ_SPIN_YIELD() ::rjb::tile::emu_yield()
-namespace rjb
-{
-  namespace tile
-  {
-    void emu_yield();
-  }
-  template <typename Kernel>
-  inline int rj_cooperative_grid_limit(Kernel, int, int)
-  {
-    return 1;
-  }
-} // namespace rjb

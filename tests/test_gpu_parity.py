@@ -650,11 +650,12 @@ def test_streaming_transfers_match_the_blocking_ones():
 
 @pytest.mark.parametrize("setup", ["euler sod2d erk33", "euler vortex3d ssprk33", "euler sod2d erk54 iterations1",
                                    "euler_aeos sod2d erk33", "shallow_water dam erk33"])
-def test_fused_update_kernel_is_bit_identical(setup, monkeypatch):
-    """kernels_fused.cuh: on small single-rank meshes a device-resident cycle runs prepare + step of
-    every substep as ONE persistent kernel with grid-wide barriers (RYUJIN_B200_FUSED=1; automatic
-    below 262144 rows).  Same bodies, same order: state, tau sequence and counters must be the bits of
-    the separate kernels (RYUJIN_B200_FUSED=0), with a fraction of the launches."""
+def test_folded_scalar_kernels_are_bit_identical(setup, monkeypatch):
+    """Single-rank device-resident cycles fold the scalar kernels of a substep (reset, tau_local,
+    tau_finalize, cycle_record) into the sweeps around them (k_dii_tau_final, k_high_order_record: the block
+    that finishes last does the scalar work) and run d_ij + alpha as one launch on small meshes:
+    42 -> 27 launches per ERK33 cycle.  Same state, tau sequence and restart / warning counters as with the
+    separate kernels (RYUJIN_B200_FOLD=0), bang-bang restarts included."""
     import ryujin_b200 as rj
     from helpers import make_sw_product
 
@@ -662,8 +663,8 @@ def test_fused_update_kernel_is_bit_identical(setup, monkeypatch):
     equation, case, scheme = words[0], words[1], words[2]
     params = {"limiter_iterations": 1} if "iterations1" in words else None
     results = {}
-    for fused in ("0", "1"):
-        monkeypatch.setenv("RYUJIN_B200_FUSED", fused)
+    for fold in ("0", "1"):
+        monkeypatch.setenv("RYUJIN_B200_FOLD", fold)
         if equation == "shallow_water":
             od, module = make_sw_product("sw_dam2d_friction", [24, 20])
         else:
@@ -677,11 +678,9 @@ def test_fused_update_kernel_is_bit_identical(setup, monkeypatch):
             tau = ti.step(state, t)
             taus.append(tau)
             t += tau
-        results[fused] = (state.download(), np.array(taus), module.n_restarts(), module.n_warnings(),
-                          module.kernel_launches() - launches0)
+        results[fold] = (state.download(), np.array(taus), module.n_restarts(), module.n_warnings(),
+                         module.kernel_launches() - launches0)
     U0, taus0, nr0, nw0, launches_separate = results["0"]
-    U1, taus1, nr1, nw1, launches_fused = results["1"]
+    U1, taus1, nr1, nw1, launches_folded = results["1"]
     assert np.array_equal(U1, U0) and np.array_equal(taus1, taus0) and (nr1, nw1) == (nr0, nw0)
-    # erk 54: the substeps with 3 and 4 stage states take the separate kernels (RJ_FUSED_MAX_STAGES = 2)
-    factor = 1 if "erk54" in words else 3
-    assert launches_fused * factor < launches_separate, (launches_fused, launches_separate)
+    assert launches_folded * 4 <= launches_separate * 3, (launches_folded, launches_separate)

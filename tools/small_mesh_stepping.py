@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Meshes that do not fill the GPU are bound by launch / dependency latency: time one ERK33 cycle with
 the ways of driving it -- reference control flow (host), device-resident cycle, CUDA graph replay -- with all
-14 kernels of an update launched separately (RYUJIN_B200_FOLD=0), with the scalar kernels folded into the
-sweeps and d_ij + alpha as one launch (the default), and with one persistent kernel per update
-(kernels_fused.cuh, RYUJIN_B200_FUSED=1), over a range of mesh sizes.  Checksums must agree between all modes of a mesh (bit-identical paths)."""
+14 kernels of an update launched separately (RYUJIN_B200_FOLD=0) and with the scalar kernels folded into the
+sweeps and d_ij + alpha as one launch (the default), over a range of mesh sizes.  (A third way, one
+persistent cooperative kernel per update with grid-wide barriers, was built and measured in round 2 --
+profiles/r2i_small_mesh_fused_kernel.txt, r2j_small_mesh_fused8.txt: 464 us against 392 us per cycle on
+config 1, slower at every size -- and removed.)  Checksums must agree between all modes of a mesh (bit-identical paths)."""
 import json
 import os
 import sys
@@ -22,9 +24,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--quick":
     MESHES = MESHES[:1] + MESHES[4:5]
 
 CONFIGS = [  # label, environment, stepping modes
-    ("", dict(RYUJIN_B200_FOLD="0", RYUJIN_B200_FUSED="0"), (rj.Stepping.host, rj.Stepping.device, rj.Stepping.graph)),
-    (" folded", dict(RYUJIN_B200_FOLD="1", RYUJIN_B200_FUSED="0"), (rj.Stepping.device, rj.Stepping.graph)),  # the default
-    (" fused", dict(RYUJIN_B200_FOLD="1", RYUJIN_B200_FUSED="1"), (rj.Stepping.graph,)),
+    ("", dict(RYUJIN_B200_FOLD="0"), (rj.Stepping.host, rj.Stepping.device, rj.Stepping.graph)),
+    (" folded", dict(RYUJIN_B200_FOLD="1"), (rj.Stepping.device, rj.Stepping.graph)),  # the default
 ]
 out = {}
 for case, n in MESHES:
