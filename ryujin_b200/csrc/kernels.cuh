@@ -102,6 +102,18 @@
 #define RJ_MB_HO 6
 #endif
 
+/* L2 prefetch of the streamed matrix side (cols, c_ij, d_ij, edge cache) of the row-parallel sweeps
+ * RJ_L2_PREFETCH columns ahead: the entries of a slice are one contiguous run per array, a column further is
+ * 256 bytes further.  No registers, no shared memory; 0 = off */
+#ifndef RJ_L2_PREFETCH
+#define RJ_L2_PREFETCH 0
+#endif
+#if defined(__CUDA_ARCH__)
+#define RJ_PREFETCH_L2(pointer) asm volatile("prefetch.global.L2 [%0];" ::"l"(pointer))
+#else
+#define RJ_PREFETCH_L2(pointer) ((void)(pointer))
+#endif
+
 namespace rjb
 {
   struct StencilView {
@@ -479,6 +491,15 @@ namespace rjb
     for (uint32_t col = 0; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
       const uint32_t j = RJ_INDEX(RJ_PREFETCH_ALPHA, j_next, v.cols, e, col, r.len);
+      if (RJ_L2_PREFETCH > 0 && col + RJ_L2_PREFETCH < r.len) {
+        const uint32_t ahead = e + 32 * RJ_L2_PREFETCH;
+        RJ_PREFETCH_L2(&v.cols[ahead]);
+#pragma unroll
+        for (int d = 0; d < dim; ++d)
+          RJ_PREFETCH_L2(&v.cij[size_t(d) * v.E_owned + ahead]);
+        if constexpr (do_cache)
+          RJ_PREFETCH_L2(&v.transposed[ahead]);
+      }
       double U_j[k], prec_j[np], aux_j[na], c_ij[dim];
       load_state<k>(U, v.ld, j, U_j);
       load_state<np>(prec, v.ld, j, prec_j);
@@ -860,6 +881,16 @@ namespace rjb
     for (uint32_t col = 0; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
       const uint32_t j = RJ_INDEX(RJ_PREFETCH_LOW, j_next, v.cols, e, col, r.len);
+      if (RJ_L2_PREFETCH > 0 && col + RJ_L2_PREFETCH < r.len) {
+        const uint32_t ahead = e + 32 * RJ_L2_PREFETCH;
+        RJ_PREFETCH_L2(&v.cols[ahead]);
+#pragma unroll
+        for (int d = 0; d < dim; ++d)
+          RJ_PREFETCH_L2(&v.cij[size_t(d) * v.E_owned + ahead]);
+        RJ_PREFETCH_L2(&dij[ahead]);
+        if constexpr (cached)
+          RJ_PREFETCH_L2(&edge_cache[ahead]);
+      }
 
       double U_j[k], prec_j[np], c_ij[dim];
       load_state<k>(U, v.ld, j, U_j);

@@ -36,7 +36,8 @@ METRICS = [
     ("sm__cycles_active.avg", "sm cycles active (avg)"),
 ]
 SLOT = [("k_dij", "dij"), ("k_alpha", "alpha"), ("k_low_order", "low_order"), ("k_pij_lij", "pij_lij"),
-        ("k_high_order_tile", "high_order_next_lij"), ("k_high_order<", "high_order_final"), ("k_dii_tau", "dii_tau")]
+        ("k_high_order_tile", "high_order_next_lij"), ("k_high_order_record", "high_order_final"),
+        ("k_high_order<", "high_order_final"), ("k_dii_tau", "dii_tau")]
 
 
 def short(name):
