@@ -86,6 +86,9 @@
 #ifndef RJ_MB_ALPHA
 #define RJ_MB_ALPHA 8
 #endif
+#ifndef RJ_MB_DIJ_ALPHA
+#define RJ_MB_DIJ_ALPHA 8 /* the merged step-2 launch (k_dij_alpha) */
+#endif
 #ifndef RJ_MB_ALPHA_CACHE
 #define RJ_MB_ALPHA_CACHE 6 /* with the edge cache (one pow per entry j > i): 8 -> 3.56 ms, 6 -> 3.69, 5 -> 4.69 next to step 4 at 6.42 / 6.29 / 6.19 */
 #endif
@@ -106,12 +109,23 @@
  * RJ_L2_PREFETCH columns ahead: the entries of a slice are one contiguous run per array, a column further is
  * 256 bytes further.  No registers, no shared memory; 0 = off */
 #ifndef RJ_L2_PREFETCH
-#define RJ_L2_PREFETCH 0
+#define RJ_L2_PREFETCH 2 /* B200, 8M DoFs: step 4 6.17 -> 5.77 / 5.46 / 5.60 / 5.66 / 5.70 ms for 1 .. 5 columns, k_alpha 3.58 -> 3.39 */
+#endif
+#ifndef RJ_L2_PREFETCH_LOW
+#define RJ_L2_PREFETCH_LOW RJ_L2_PREFETCH
+#endif
+#ifndef RJ_L2_PREFETCH_ALPHA
+#define RJ_L2_PREFETCH_ALPHA RJ_L2_PREFETCH
+#endif
+#ifndef RJ_GATHER_PREFETCH
+#define RJ_GATHER_PREFETCH 0 /* experiment: prefetch.global.L1 of the next column's neighbour state in step 4 */
 #endif
 #if defined(__CUDA_ARCH__)
 #define RJ_PREFETCH_L2(pointer) asm volatile("prefetch.global.L2 [%0];" ::"l"(pointer))
+#define RJ_PREFETCH_L1(pointer) asm volatile("prefetch.global.L1 [%0];" ::"l"(pointer))
 #else
 #define RJ_PREFETCH_L2(pointer) ((void)(pointer))
+#define RJ_PREFETCH_L1(pointer) ((void)(pointer))
 #endif
 
 namespace rjb
@@ -491,8 +505,8 @@ namespace rjb
     for (uint32_t col = 0; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
       const uint32_t j = RJ_INDEX(RJ_PREFETCH_ALPHA, j_next, v.cols, e, col, r.len);
-      if (RJ_L2_PREFETCH > 0 && col + RJ_L2_PREFETCH < r.len) {
-        const uint32_t ahead = e + 32 * RJ_L2_PREFETCH;
+      if (RJ_L2_PREFETCH_ALPHA > 0 && col + RJ_L2_PREFETCH_ALPHA < r.len) {
+        const uint32_t ahead = e + 32 * RJ_L2_PREFETCH_ALPHA;
         RJ_PREFETCH_L2(&v.cols[ahead]);
 #pragma unroll
         for (int d = 0; d < dim; ++d)
@@ -537,12 +551,16 @@ namespace rjb
    * heterogeneous blocks -- blocks [0, n_slices) run the edge-parallel d_ij body, the rest the row-parallel
    * indicator -- one dependency latency less per update where launches, not bandwidth, bound the update. */
   template <class Eq, bool alpha_cache>
-  __global__ void __launch_bounds__(128, RJ_MB_ALPHA) k_dij_alpha(StencilView v, typename Eq::Params prm, uint32_t n_slices, const double *__restrict__ U, const double *__restrict__ prec, const double *__restrict__ aux, double *__restrict__ dij, double *__restrict__ alpha, double *__restrict__ edge_cache)
+  __global__ void __launch_bounds__(128, RJ_MB_DIJ_ALPHA) k_dij_alpha(StencilView v, typename Eq::Params prm, uint32_t n_slices, const double *__restrict__ U, const double *__restrict__ prec, const double *__restrict__ aux, double *__restrict__ dij, double *__restrict__ alpha, double *__restrict__ edge_cache)
   {
-    if (blockIdx.x < n_slices)
-      dij_body<Eq, 4>(blockIdx.x, v, prm, 0u, n_slices, U, prec, dij);
+    /* groups of five blocks: four slices of the d_ij body and the row block (128 rows = the same four
+     * slices) of the indicator body, so that the FP64-issue bound solves and the latency bound gathers of
+     * step 2 are resident on an SM at the same time; grid = 5 * ceil(n_owned / 128) */
+    const uint32_t group = blockIdx.x / 5, role = blockIdx.x % 5;
+    if (role < 4)
+      dij_body<Eq, 4>(4 * group + role, v, prm, 0u, n_slices, U, prec, dij);
     else
-      alpha_body<Eq, alpha_cache>(blockIdx.x - n_slices, v, prm, 0u, v.n_owned, U, prec, aux, alpha, edge_cache);
+      alpha_body<Eq, alpha_cache>(group, v, prm, 0u, v.n_owned, U, prec, aux, alpha, edge_cache);
   }
 
   /* Step 3a: complete d_ij on coupling boundary pairs (i < j),
@@ -881,8 +899,8 @@ namespace rjb
     for (uint32_t col = 0; col < r.len; ++col) {
       const uint32_t e = r.base + col * 32;
       const uint32_t j = RJ_INDEX(RJ_PREFETCH_LOW, j_next, v.cols, e, col, r.len);
-      if (RJ_L2_PREFETCH > 0 && col + RJ_L2_PREFETCH < r.len) {
-        const uint32_t ahead = e + 32 * RJ_L2_PREFETCH;
+      if (RJ_L2_PREFETCH_LOW > 0 && col + RJ_L2_PREFETCH_LOW < r.len) {
+        const uint32_t ahead = e + 32 * RJ_L2_PREFETCH_LOW;
         RJ_PREFETCH_L2(&v.cols[ahead]);
 #pragma unroll
         for (int d = 0; d < dim; ++d)
@@ -890,6 +908,16 @@ namespace rjb
         RJ_PREFETCH_L2(&dij[ahead]);
         if constexpr (cached)
           RJ_PREFETCH_L2(&edge_cache[ahead]);
+      }
+      if (RJ_GATHER_PREFETCH && RJ_PREFETCH_LOW && col + 1 < r.len) {
+#pragma unroll
+        for (int q = 0; q < k; ++q)
+          RJ_PREFETCH_L1(&U[size_t(q) * v.ld + j_next]);
+        RJ_PREFETCH_L1(&prec[j_next]);
+#pragma unroll
+        for (int q = 0; q < na; ++q)
+          RJ_PREFETCH_L1(&aux[size_t(q) * v.ld + j_next]);
+        RJ_PREFETCH_L1(&alpha[j_next]);
       }
 
       double U_j[k], prec_j[np], c_ij[dim];

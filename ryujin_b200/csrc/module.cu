@@ -834,7 +834,7 @@ namespace rjb
       tag(P_DIJ);
       const bool merged_step2 = folded && !profiling && n_owned <= small_mesh_rows;
       if (merged_step2) {
-        launch(k_dij_alpha<Eq, use_edge_cache>, (size_t(od->n_slices) + (n_owned + 127) / 128) * 128, 128, v, prm, od->n_slices,
+        launch(k_dij_alpha<Eq, use_edge_cache>, size_t(5) * ((n_owned + 127) / 128) * 128, 128, v, prm, od->n_slices,
                old_state.U, old_state.prec, old_state.aux, dij, alpha, edge_cache);
       } else {
         constexpr int W = RJ_DIJ_W; /* warps per slice in the edge-parallel d_ij kernel */
