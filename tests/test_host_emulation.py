@@ -35,6 +35,14 @@ def run_gpu_tests(selection, timeout=900):
     env = dict(os.environ, RYUJIN_B200_LIB=EMU_LIB)  # default stepping: CUDA graph replay (capture is emulated)
     cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-q", "-m", "gpu", "-k", selection,
            "-p", "no:cacheprovider"]
+    try:  # the emulated tests are independent processes' worth of work: spread them over a few cores
+        import xdist  # noqa: F401
+
+        workers = max(1, min(4, (os.cpu_count() or 2) // 2))
+        cmd += ["-n", str(workers)]
+        env["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 2) // workers))  # the oracle is OpenMP parallel
+    except ImportError:
+        pass
     out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
     return out.returncode, out.stdout + out.stderr
 
