@@ -117,15 +117,10 @@
 #ifndef RJ_L2_PREFETCH_ALPHA
 #define RJ_L2_PREFETCH_ALPHA RJ_L2_PREFETCH
 #endif
-#ifndef RJ_GATHER_PREFETCH
-#define RJ_GATHER_PREFETCH 0 /* experiment: prefetch.global.L1 of the next column's neighbour state in step 4 */
-#endif
 #if defined(__CUDA_ARCH__)
 #define RJ_PREFETCH_L2(pointer) asm volatile("prefetch.global.L2 [%0];" ::"l"(pointer))
-#define RJ_PREFETCH_L1(pointer) asm volatile("prefetch.global.L1 [%0];" ::"l"(pointer))
 #else
 #define RJ_PREFETCH_L2(pointer) ((void)(pointer))
-#define RJ_PREFETCH_L1(pointer) ((void)(pointer))
 #endif
 
 namespace rjb
@@ -908,16 +903,6 @@ namespace rjb
         RJ_PREFETCH_L2(&dij[ahead]);
         if constexpr (cached)
           RJ_PREFETCH_L2(&edge_cache[ahead]);
-      }
-      if (RJ_GATHER_PREFETCH && RJ_PREFETCH_LOW && col + 1 < r.len) {
-#pragma unroll
-        for (int q = 0; q < k; ++q)
-          RJ_PREFETCH_L1(&U[size_t(q) * v.ld + j_next]);
-        RJ_PREFETCH_L1(&prec[j_next]);
-#pragma unroll
-        for (int q = 0; q < na; ++q)
-          RJ_PREFETCH_L1(&aux[size_t(q) * v.ld + j_next]);
-        RJ_PREFETCH_L1(&alpha[j_next]);
       }
 
       double U_j[k], prec_j[np], c_ij[dim];
